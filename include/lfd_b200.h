@@ -1,0 +1,204 @@
+/* lfd_b200.h - C ABI of the B200-native lfd.detecttrails per-frame detection library.
+ *
+ * The reference (DinoBektesevic/lfd) is pure Python and has no FFI for this path; its boundary
+ * is the set of Python call signatures listed below.  Each entry point here replaces the device-
+ * worthy part of one of them and is what a reference-side ctypes stub binds.
+ * Paths are relative to /root/reference/.
+ *
+ *   lfd_submit + lfd_wait      replaces the body of process_field()
+ *                                lfd/detecttrails/detecttrails.py:119-131
+ *                              = remove_stars blot      lfd/detecttrails/removestars.py:231
+ *                              + cv2.flip(img, 0)       lfd/detecttrails/detecttrails.py:124
+ *                              + process_field_bright   lfd/detecttrails/processfield.py:291-388
+ *                              + process_field_dim      lfd/detecttrails/processfield.py:391-506
+ *   lfd_run_pass               one of process_field_bright / process_field_dim on an already
+ *                              flipped frame (their public, directly callable form,
+ *                              processfield.py:15 __all__), optional in-place write-back of the
+ *                              clipped float image (processfield.py:342, :453-454)
+ *   lfd_blot                   remove_stars' in-place square fill, removestars.py:231
+ *   lfd_get_stage              the debug taps of processfield.py:349-378, :459-496 as raw arrays
+ *   lfd_hough_lines            cv2.HoughLines(img, rho, theta, threshold) as called at
+ *                              processfield.py:370-371, :488-489 (also the config-5 microbench)
+ *   lfd_set_params             the params_bright / params_dim dicts,
+ *                              lfd/detecttrails/detecttrails.py:202-230
+ *
+ * Conventions: every call returns 0 on success or a negative LFD_E_* code; lfd_last_error()
+ * gives the text.  The caller owns all host buffers; the library owns all device memory and
+ * streams.  A handle is bound to one GPU and is not thread-safe (one handle per host worker).
+ * No C++ types and no exceptions cross this boundary.  There is no CPU fallback: without a
+ * CUDA device lfd_create fails with LFD_E_CUDA.
+ */
+#ifndef LFD_B200_H
+#define LFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFD_ABI_VERSION 1
+
+/* error codes */
+#define LFD_OK 0
+#define LFD_E_ARG (-1)          /* bad argument */
+#define LFD_E_CUDA (-2)         /* CUDA runtime error (text in lfd_last_error) */
+#define LFD_E_UNSUPPORTED (-3)  /* legal reference parameter this build does not implement */
+#define LFD_E_CAPACITY (-4)     /* a per-frame work list overflowed its configured capacity */
+#define LFD_E_STATE (-5)        /* call order violated (e.g. wait without submit) */
+
+/* per-frame status bits in lfd_result.status */
+#define LFD_FRAME_OK 0
+#define LFD_FRAME_OVERFLOW 1        /* run/component/peak list overflow: result invalid */
+#define LFD_FRAME_NO_LINES_EQU 2    /* HoughLines(equ) returned no line: the reference raises TypeError */
+#define LFD_FRAME_NO_LINES_BOX 4    /* HoughLines(box_img) returned no line: likewise */
+
+/* passes */
+#define LFD_PASS_BRIGHT 0
+#define LFD_PASS_DIM 1
+
+/* lfd_submit flags */
+#define LFD_INPUT_NATIVE 0      /* host float32, native byte order (what fitsio.read returns) */
+#define LFD_INPUT_BIGENDIAN 1   /* raw FITS payload: big-endian float32, byte-swapped on the device */
+#define LFD_KEEP_TAPS 2         /* materialise the uint8 stage images for lfd_get_stage */
+#define LFD_FULL_LINES 4        /* sort and keep the full HoughLines lists (taps / parity) */
+
+/* stage ids for lfd_get_stage (uint8 H*W unless noted) */
+enum lfd_stage {
+    LFD_STAGE_MASK = 0,      /* star mask, 255 where blotted, in the flipped orientation */
+    LFD_STAGE_GRAY = 1,      /* convertScaleAbs output          processfield.py:346,456 */
+    LFD_STAGE_EQU = 2,       /* equalizeHist output             processfield.py:347,457 */
+    LFD_STAGE_ERODED = 3,    /* erode output (dim only)         processfield.py:464     */
+    LFD_STAGE_MORPH = 4,     /* dilate output = Canny/Hough input  processfield.py:354,471 */
+    LFD_STAGE_CANNY = 5,     /* Canny(.,0,255)                  processfield.py:236     */
+    LFD_STAGE_BOX = 6,       /* box_img                         processfield.py:235,261 */
+    LFD_STAGE_HIST = 7,      /* uint32[256] histogram of GRAY */
+    LFD_STAGE_LUT = 8,       /* uint8[256] equalisation LUT */
+    LFD_STAGE_NMS = 9,       /* uint8 H*W: 0 none, 1 weak, 2 strong after non-maximum suppression */
+    LFD_STAGE_FG_LABELS = 10,/* int32 H*W: raster-first pixel index of the 8-connected edge component, -1 elsewhere */
+    LFD_STAGE_BG_LABELS = 11,/* int32 H*W: raster-first pixel index of the 4-connected hole, -2 outside background, -1 on edges */
+    LFD_STAGE_RECTS = 12,    /* lfd_rect[n]; count via lfd_get_stage_count */
+    LFD_STAGE_ACCUM_EQU = 13,/* int32 (numangle+2)*(numrho+2) Hough accumulator of MORPH */
+    LFD_STAGE_ACCUM_BOX = 14,/* same for BOX */
+    LFD_STAGE_LINES_EQU = 15,/* float32[n][2] (rho, theta) in cv2.HoughLines order; needs LFD_FULL_LINES */
+    LFD_STAGE_LINES_BOX = 16,
+    LFD_STAGE_CLIPPED = 17   /* float32 H*W: the frame after the pass's in-place clip (processfield.py:342,453-454) */
+};
+
+/* one pass's parameters: the keys of params_bright / params_dim (detecttrails.py:202-230) */
+typedef struct lfd_pass_params {
+    double lwTresh;
+    double thetaTresh;
+    double lineSetTresh;
+    double dro;
+    double minAreaRectMinLen;
+    double houghMethod;         /* = rho of cv2.HoughLines (processfield.py:370) */
+    double minFlux;             /* dim only */
+    double addFlux;             /* dim only */
+    int32_t nlinesInSet;        /* <= LFD_MAX_SET_LINES */
+    int32_t contoursMode;       /* cv2.RETR_*: LIST(1) and CCOMP(2), TREE(3) give the same set; EXTERNAL(0) unsupported */
+    int32_t contoursMethod;     /* cv2.CHAIN_APPROX_NONE(1) or SIMPLE(2) (same hulls); TC89_* unsupported */
+    int32_t erode_h, erode_w;   /* 0,0 = no erosion (bright).  Kernels must be all-ones rectangles. */
+    int32_t dilate_h, dilate_w;
+    int32_t reserved;
+} lfd_pass_params;
+
+typedef struct lfd_params {
+    lfd_pass_params bright;
+    lfd_pass_params dim;
+} lfd_params;
+
+#define LFD_MAX_SET_LINES 16
+
+/* per-frame outcome of lfd_submit/lfd_wait or lfd_run_pass */
+typedef struct lfd_result {
+    int32_t detected;           /* 1 if a pass accepted a line */
+    int32_t pass;               /* LFD_PASS_BRIGHT / LFD_PASS_DIM that detected, else -1 */
+    int32_t status;             /* LFD_FRAME_* bits */
+    int32_t rect_detection[2];  /* per pass: fit_minAreaRect's `detection` (processfield.py:258); -1 = pass not run */
+    int32_t n_lines_equ[2];     /* per pass: len(HoughLines(equ)), -1 if Hough did not run */
+    int32_t n_lines_box[2];
+    int32_t rejected[2];        /* per pass: 1 if check_theta returned True (processfield.py:380,498) */
+    float rho;                  /* equhough[0][0] of the detecting pass (processfield.py:384,502) */
+    float theta;
+    float top_equ[2][LFD_MAX_SET_LINES][2]; /* per pass: first nlinesInSet (rho,theta) of HoughLines(equ) */
+    float top_box[2][LFD_MAX_SET_LINES][2];
+} lfd_result;
+
+/* a minimum-area rectangle as cv2.minAreaRect returns it (processfield.py:249) */
+typedef struct lfd_rect {
+    float cx, cy, w, h, angle;
+    int32_t kind;               /* 0 = outer border of an edge component, 1 = hole border */
+    int32_t key;                /* raster-first pixel index (y*W+x) of the component / hole */
+    int32_t passed;             /* 1 if it passed the length/width filter (processfield.py:256-257) */
+    int32_t box[8];             /* int32(boxPoints(rect)) x0,y0..x3,y3 (processfield.py:259-260); valid if passed */
+} lfd_rect;
+
+/* optional capacities for lfd_create_ex (0 = default) */
+typedef struct lfd_config {
+    int32_t max_runs;           /* runs per frame and mask kind (default 1<<20) */
+    int32_t max_components;     /* contours per frame and kind (default 1<<18) */
+    int32_t max_star_rects;     /* blot squares per frame (default 8192) */
+    int32_t max_lines;          /* HoughLines entries kept per frame in LFD_FULL_LINES mode (default numangle*numrho) */
+    int32_t reserved[4];
+} lfd_config;
+
+typedef struct lfd_handle lfd_handle;
+
+int lfd_abi_version(void);
+
+/* Create a handle on CUDA device `device` for batches of up to `max_batch` frames of height x width. */
+int lfd_create(int device, int max_batch, int height, int width, lfd_handle** out);
+int lfd_create_ex(int device, int max_batch, int height, int width, const lfd_config* cfg, lfd_handle** out);
+int lfd_destroy(lfd_handle* h);
+const char* lfd_last_error(const lfd_handle* h);   /* h may be NULL: error of the last failed lfd_create */
+
+int lfd_set_params(lfd_handle* h, const lfd_params* p);
+
+/* Pinned host staging owned by the library (frames in, `max_batch` slots of height*width float32). */
+int lfd_host_frames(lfd_handle* h, float** out);
+
+/* Whole-frame path.  `frames`: n un-flipped float32 frames (FITS orientation), contiguous; pass NULL to use
+ * the library's own pinned staging (lfd_host_frames).  `rects`: blot squares as (row_start,row_stop,col_start,
+ * col_stop) half-open quadruples on the UN-flipped image, already resolved by the host to Python slice
+ * semantics (removestars.py:231); rect_offsets[n+1] indexes them per frame.  Asynchronous. */
+int lfd_submit(lfd_handle* h, const float* frames, int n, const int32_t* rects, const int32_t* rect_offsets, int flags);
+int lfd_wait(lfd_handle* h, lfd_result* out /* n entries */);
+
+/* Device-resident variant used by the benchmark's `value` leg: runs the same pipeline on the frames
+ * uploaded by the previous lfd_submit/lfd_upload without any host<->device copy of pixel data. */
+int lfd_upload(lfd_handle* h, const float* frames, int n, const int32_t* rects, const int32_t* rect_offsets, int flags);
+int lfd_run_resident(lfd_handle* h, int n, int flags);
+
+/* One pass on one already flipped frame (process_field_bright / process_field_dim called directly).
+ * If `writeback` != 0 the clipped float image is copied back into `img` (the reference mutates it). */
+int lfd_run_pass(lfd_handle* h, int pass, float* img, int flags, int writeback, lfd_result* out);
+
+/* remove_stars' blot on a host image, in place (UN-flipped orientation, same rect convention as lfd_submit). */
+int lfd_blot(lfd_handle* h, float* img, const int32_t* rects, int nrects);
+
+/* Stage taps of the last run; `frame` indexes the batch, `pass` is LFD_PASS_*. */
+int lfd_get_stage(lfd_handle* h, int frame, int pass, int stage, void* host_out, size_t bytes);
+int lfd_get_stage_count(lfd_handle* h, int frame, int pass, int stage, int* count);
+
+/* cv2.HoughLines(img, rho, theta, threshold) on a host uint8 image of any size.
+ * lines: float32[max_lines][2]; accum (optional): int32[(numangle+2)*(numrho+2)]; returns the total
+ * number of lines in *n_lines (may exceed max_lines; only max_lines are written). */
+int lfd_hough_dims(int height, int width, double rho, double theta, int* numangle, int* numrho);
+int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, double rho, double theta,
+                    int threshold, float* lines, int max_lines, int* n_lines, int32_t* accum);
+
+/* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
+int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
+const char* lfd_timing_name(int i);
+/* Number of kernels this library launched since the handle was created. */
+int64_t lfd_kernel_launches(const lfd_handle* h);
+/* Work counters of the last run, summed over the batch: [0] nonzero px voted equ, [1] box, [2] votes,
+ * [3] runs fg, [4] runs bg, [5] contours, [6] passing rects, [7] frames that ran dim, [8] frames that ran Hough. */
+int lfd_get_counters(lfd_handle* h, int64_t* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFD_B200_H */

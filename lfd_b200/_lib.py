@@ -1,0 +1,333 @@
+"""ctypes binding of liblfd_b200.so (include/lfd_b200.h).  No torch, no cv2, no CPU fallback:
+if the CUDA library is missing or no GPU is present the import of the library / creation of a
+handle raises and the caller sees it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "liblfd_b200.so")
+SRC = os.path.join(HERE, "csrc", "lfd_b200.cu")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+LFD_OK, LFD_E_ARG, LFD_E_CUDA, LFD_E_UNSUPPORTED, LFD_E_CAPACITY, LFD_E_STATE = 0, -1, -2, -3, -4, -5
+FRAME_OVERFLOW, FRAME_NO_LINES_EQU, FRAME_NO_LINES_BOX = 1, 2, 4
+PASS_BRIGHT, PASS_DIM = 0, 1
+INPUT_NATIVE, INPUT_BIGENDIAN, KEEP_TAPS, FULL_LINES = 0, 1, 2, 4
+MAX_SET_LINES = 16
+
+STAGES = {"mask": 0, "gray": 1, "equ": 2, "eroded": 3, "morph": 4, "canny": 5, "box": 6, "hist": 7, "lut": 8,
+          "nms": 9, "fg_labels": 10, "bg_labels": 11, "rects": 12, "accum_equ": 13, "accum_box": 14,
+          "lines_equ": 15, "lines_box": 16, "clipped": 17}
+
+
+class PassParams(ctypes.Structure):
+    _fields_ = [("lwTresh", ctypes.c_double), ("thetaTresh", ctypes.c_double), ("lineSetTresh", ctypes.c_double),
+                ("dro", ctypes.c_double), ("minAreaRectMinLen", ctypes.c_double), ("houghMethod", ctypes.c_double),
+                ("minFlux", ctypes.c_double), ("addFlux", ctypes.c_double), ("nlinesInSet", ctypes.c_int32),
+                ("contoursMode", ctypes.c_int32), ("contoursMethod", ctypes.c_int32),
+                ("erode_h", ctypes.c_int32), ("erode_w", ctypes.c_int32),
+                ("dilate_h", ctypes.c_int32), ("dilate_w", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("bright", PassParams), ("dim", PassParams)]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("detected", ctypes.c_int32), ("pass_", ctypes.c_int32), ("status", ctypes.c_int32),
+                ("rect_detection", ctypes.c_int32 * 2), ("n_lines_equ", ctypes.c_int32 * 2),
+                ("n_lines_box", ctypes.c_int32 * 2), ("rejected", ctypes.c_int32 * 2),
+                ("rho", ctypes.c_float), ("theta", ctypes.c_float),
+                ("top_equ", ((ctypes.c_float * 2) * MAX_SET_LINES) * 2),
+                ("top_box", ((ctypes.c_float * 2) * MAX_SET_LINES) * 2)]
+
+
+RECT_DTYPE = np.dtype([("cx", "<f4"), ("cy", "<f4"), ("w", "<f4"), ("h", "<f4"), ("angle", "<f4"),
+                       ("kind", "<i4"), ("key", "<i4"), ("passed", "<i4"), ("box", "<i4", (8,))])
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("max_runs", ctypes.c_int32), ("max_components", ctypes.c_int32), ("max_star_rects", ctypes.c_int32),
+                ("max_lines", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+
+
+class LfdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lfd_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class UnsupportedParameter(LfdError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    srcs.append(os.path.join(ROOT, "include", "lfd_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
+            return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + [SRC, "-o", LIB_PATH]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("liblfd_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.lfd_last_error.restype = ctypes.c_char_p
+        L.lfd_last_error.argtypes = [ctypes.c_void_p]
+        L.lfd_timing_name.restype = ctypes.c_char_p
+        L.lfd_kernel_launches.restype = ctypes.c_int64
+        L.lfd_kernel_launches.argtypes = [ctypes.c_void_p]
+        L.lfd_create_ex.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_void_p)]
+        L.lfd_destroy.argtypes = [ctypes.c_void_p]
+        L.lfd_set_params.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lfd_host_frames.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.lfd_submit.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lfd_upload.argtypes = L.lfd_submit.argtypes
+        L.lfd_run_resident.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.lfd_wait.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lfd_run_pass.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.lfd_blot.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lfd_get_stage.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+        L.lfd_get_stage_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.lfd_hough_dims.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                     ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.lfd_hough_lines.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        if L.lfd_abi_version() != 1:
+            raise ImportError("liblfd_b200.so ABI mismatch")
+        _lib = L
+    return _lib
+
+
+def _kernel_hw(kernel, name):
+    if kernel is None:
+        return 0, 0
+    k = np.asarray(kernel)
+    if k.ndim != 2 or k.size == 0:
+        raise ValueError("%s must be a 2-D array" % name)
+    if not np.all(k != 0):
+        raise UnsupportedParameter(LFD_E_UNSUPPORTED, "%s: only all-ones rectangular kernels are implemented" % name)
+    return int(k.shape[0]), int(k.shape[1])
+
+
+def pass_params(d, dim):
+    """params_bright / params_dim dict (reference keys, detecttrails.py:202-230) -> PassParams."""
+    p = PassParams()
+    p.lwTresh = float(d["lwTresh"])
+    p.thetaTresh = float(d["thetaTresh"])
+    p.lineSetTresh = float(d["lineSetTresh"])
+    p.dro = float(d["dro"])
+    p.minAreaRectMinLen = float(d["minAreaRectMinLen"])
+    p.houghMethod = float(d["houghMethod"])
+    p.minFlux = float(d.get("minFlux", 0.0)) if dim else 0.0
+    p.addFlux = float(d.get("addFlux", 0.0)) if dim else 0.0
+    p.nlinesInSet = int(d["nlinesInSet"])
+    p.contoursMode = int(d["contoursMode"])
+    p.contoursMethod = int(d["contoursMethod"])
+    p.erode_h, p.erode_w = _kernel_hw(d.get("erodeKernel"), "erodeKernel") if dim else (0, 0)
+    p.dilate_h, p.dilate_w = _kernel_hw(d["dilateKernel"], "dilateKernel")
+    return p
+
+
+class Handle:
+    """One GPU worker: owns device buffers for `max_batch` frames of (height, width)."""
+
+    def __init__(self, height, width, max_batch=1, device=0, max_runs=0, max_components=0, max_star_rects=0, max_lines=0):
+        L = lib()
+        self._L = L
+        self.h = ctypes.c_void_p()
+        cfg = Config(max_runs, max_components, max_star_rects, max_lines)
+        rc = L.lfd_create_ex(device, max_batch, height, width, ctypes.byref(cfg), ctypes.byref(self.h))
+        if rc != LFD_OK:
+            self.h = None
+            raise LfdError(rc, (L.lfd_last_error(None) or b"").decode())
+        self.H, self.W, self.B, self.device = height, width, max_batch, device
+        self._params_key = None
+        hp = ctypes.c_void_p()
+        self._ck(L.lfd_host_frames(self.h, ctypes.byref(hp)))
+        buf = (ctypes.c_float * (max_batch * height * width)).from_address(hp.value)
+        self.host_frames = np.frombuffer(buf, dtype=np.float32).reshape(max_batch, height, width)
+        self._results = (Result * max_batch)()
+
+    def _ck(self, rc):
+        if rc != LFD_OK:
+            msg = (self._L.lfd_last_error(self.h) or b"").decode()
+            raise (UnsupportedParameter if rc == LFD_E_UNSUPPORTED else LfdError)(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.host_frames = None
+            self._L.lfd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params_bright, params_dim):
+        key = repr((sorted((k, np.asarray(v).tolist()) for k, v in params_bright.items() if k != "debug"),
+                    sorted((k, np.asarray(v).tolist()) for k, v in params_dim.items() if k != "debug")))
+        if key == self._params_key:
+            return
+        P = Params(pass_params(params_bright, False), pass_params(params_dim, True))
+        self._ck(self._L.lfd_set_params(self.h, ctypes.byref(P)))
+        self._params_key = key
+
+    @staticmethod
+    def _rects_arrays(rects_per_frame):
+        if rects_per_frame is None:
+            return None, None, None, None
+        offs = np.zeros(len(rects_per_frame) + 1, np.int32)
+        for i, r in enumerate(rects_per_frame):
+            offs[i + 1] = offs[i] + len(r)
+        flat = np.zeros((max(int(offs[-1]), 1), 4), np.int32)
+        if offs[-1]:
+            flat[:offs[-1]] = np.concatenate([np.asarray(r, np.int32).reshape(-1, 4) for r in rects_per_frame if len(r)])
+        return flat, offs, flat.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p)
+
+    def submit(self, frames, rects_per_frame=None, flags=0):
+        """frames: (n, H, W) float32 C-contiguous host array, or an int n to use self.host_frames[:n]."""
+        if isinstance(frames, (int, np.integer)):
+            n, ptr = int(frames), None
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.float32 if not (flags & INPUT_BIGENDIAN) else frames.dtype)
+            n, ptr = frames.shape[0], frames.ctypes.data_as(ctypes.c_void_p)
+        self._keep = (frames, self._rects_arrays(rects_per_frame))
+        _, _, rp, op = self._keep[1]
+        self._ck(self._L.lfd_submit(self.h, ptr, n, rp, op, flags))
+        self._n = n
+
+    def upload(self, frames, rects_per_frame=None, flags=0):
+        if isinstance(frames, (int, np.integer)):
+            n, ptr = int(frames), None
+        else:
+            frames = np.ascontiguousarray(frames)
+            n, ptr = frames.shape[0], frames.ctypes.data_as(ctypes.c_void_p)
+        keep = self._rects_arrays(rects_per_frame)
+        self._ck(self._L.lfd_upload(self.h, ptr, n, keep[2], keep[3], flags))
+        self._ck(self._L.lfd_run_resident(self.h, n, flags))   # also drains the copy before buffers go away
+        self._n = n
+        return self.wait()
+
+    def run_resident(self, n, flags=0):
+        self._ck(self._L.lfd_run_resident(self.h, n, flags))
+        self._n = n
+
+    def wait(self):
+        self._ck(self._L.lfd_wait(self.h, ctypes.byref(self._results)))
+        self._keep = None
+        return [self._results[i] for i in range(self._n)]
+
+    def run_pass(self, pass_, img, flags=0, writeback=True):
+        if img.dtype != np.float32 or not img.flags["C_CONTIGUOUS"] or img.shape != (self.H, self.W):
+            raise ValueError("img must be a C-contiguous float32 array of shape (%d, %d)" % (self.H, self.W))
+        r = Result()
+        self._ck(self._L.lfd_run_pass(self.h, pass_, img.ctypes.data_as(ctypes.c_void_p), flags, 1 if writeback else 0,
+                                      ctypes.byref(r)))
+        self._n = 1
+        return r
+
+    def blot(self, img, rects):
+        rects = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        self._ck(self._L.lfd_blot(self.h, img.ctypes.data_as(ctypes.c_void_p), rects.ctypes.data_as(ctypes.c_void_p), len(rects)))
+        return img
+
+    def stage_count(self, frame, pass_, stage):
+        c = ctypes.c_int()
+        self._ck(self._L.lfd_get_stage_count(self.h, frame, pass_, STAGES[stage], ctypes.byref(c)))
+        return c.value
+
+    def stage(self, frame, pass_, stage):
+        sid = STAGES[stage]
+        H, W = self.H, self.W
+        if stage in ("mask", "gray", "equ", "eroded", "morph", "canny", "box", "nms"):
+            out = np.empty((H, W), np.uint8)
+        elif stage == "hist":
+            out = np.empty(256, np.uint32)
+        elif stage == "lut":
+            out = np.empty(256, np.uint8)
+        elif stage in ("fg_labels", "bg_labels"):
+            out = np.empty((H, W), np.int32)
+        elif stage == "clipped":
+            out = np.empty((H, W), np.float32)
+        elif stage == "rects":
+            out = np.zeros(self.stage_count(frame, pass_, stage), RECT_DTYPE)
+        elif stage in ("accum_equ", "accum_box"):
+            out = np.empty(self.stage_count(frame, pass_, stage), np.int32)
+        elif stage in ("lines_equ", "lines_box"):
+            out = np.empty((max(self.stage_count(frame, pass_, stage), 0), 1, 2), np.float32)
+        else:
+            raise KeyError(stage)
+        if out.size:
+            self._ck(self._L.lfd_get_stage(self.h, frame, pass_, sid, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def hough_lines(self, img, rho, theta, threshold, want_accum=False, max_lines=None):
+        """cv2.HoughLines(img, rho, theta, threshold) -> (lines (n,1,2) float32 | None, accum | None)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        Hh, Ww = img.shape
+        na, nr = ctypes.c_int(), ctypes.c_int()
+        self._L.lfd_hough_dims(Hh, Ww, float(rho), float(theta), ctypes.byref(na), ctypes.byref(nr))
+        cap = na.value * nr.value if max_lines is None else max_lines
+        lines = np.empty((cap, 2), np.float32)
+        accum = np.empty((na.value + 2, nr.value + 2), np.int32) if want_accum else None
+        n = ctypes.c_int()
+        self._ck(self._L.lfd_hough_lines(self.h, img.ctypes.data_as(ctypes.c_void_p), Hh, Ww, float(rho), float(theta),
+                                         int(threshold), lines.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n),
+                                         accum.ctypes.data_as(ctypes.c_void_p) if want_accum else None))
+        k = min(n.value, cap)
+        return (lines[:k].reshape(k, 1, 2).copy() if k else None), accum
+
+    def timings(self):
+        ms = (ctypes.c_float * 32)()
+        n = ctypes.c_int()
+        self._ck(self._L.lfd_get_timings(self.h, ms, 32, ctypes.byref(n)))
+        return [(self._L.lfd_timing_name(i).decode(), float(ms[i])) for i in range(n.value)]
+
+    def counters(self):
+        c = (ctypes.c_int64 * 16)()
+        self._ck(self._L.lfd_get_counters(self.h, c, 16))
+        names = ["nnz_equ", "nnz_box", "votes", "runs_fg", "runs_bg", "contours", "passing_rects", "frames_dim",
+                 "frames_hough", "frames_bright_run", "frames_dim_run"]
+        return {k: int(c[i]) for i, k in enumerate(names)}
+
+    def kernel_launches(self):
+        return int(self._L.lfd_kernel_launches(self.h))
+
+
+_default = {}
+
+
+def default_handle(height, width, device=0):
+    """Process-wide single-frame handle used by the drop-in functions (one per frame shape and device)."""
+    key = (height, width, device)
+    h = _default.get(key)
+    if h is None:
+        h = Handle(height, width, max_batch=1, device=device)
+        _default[key] = h
+    return h

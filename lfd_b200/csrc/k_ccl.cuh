@@ -1,0 +1,402 @@
+// k_ccl.cuh - run-based union-find connected components on bit masks.
+//
+// Replaces cv2.findContours(canny, RETR_LIST, CHAIN_APPROX_NONE)
+// (/root/reference/lfd/detecttrails/processfield.py:241-246) by its structural equivalent
+// (pinned in tests/test_oracle_cv.py::test_contour_sets_rects_box_img):
+//   * one "outer" contour per 8-connected component of the edge map  -> kind 0 (fg)
+//   * one "hole" contour per 4-connected background component that does not reach the frame border;
+//     its points are the edge pixels 4-adjacent to the hole                                  -> kind 1 (bg)
+// and doubles as Canny's hysteresis: the fg pass labels the NMS *candidates*; a component is an edge
+// component iff it contains a strong pixel.
+//
+// Unit of work is a run (maximal horizontal span of set bits in one mask row), not a pixel: a
+// 2048x1489 frame has ~10^5 runs against 3*10^6 pixels.  Runs get raster-order ids
+// (row base + rank in row), so the root of a component (minimum id) is its raster-first run.
+// Kernels are launched with one warp per mask row; lanes stride over the runs of the row.
+#pragma once
+#include "common.cuh"
+
+struct CclBuf {
+    Run* runs;        // [maxruns]
+    int* parent;      // [maxruns]
+    int* flag;        // [maxruns]  fg: bit0 = component holds a strong pixel; bg: bit0 = touches the border
+    int* ymax;        // [maxruns]  valid at roots
+    int* compidx;     // [maxruns]  valid at roots: contour index or -1
+    int* rowbase;     // [H+1]
+    u16* wpre;        // [H*WW]  run starts in the words before word w of the row
+    int* rowcnt;      // [H]
+};
+
+// mask word w of row y for kind 0 (as is) / kind 1 (complement, tail bits cleared)
+__device__ __forceinline__ u32 ccl_word(const u32* __restrict__ m, int y, int w, Dims d, int kind)
+{
+    if (w < 0 || w >= d.WW) return 0u;
+    u32 v = m[(size_t)y * d.WW + w];
+    return kind ? (~v & tail_mask(w, d.W)) : v;
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int i)
+{
+    int p;
+    while ((p = __ldcg(&parent[i])) != i) i = p;
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b)
+{
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+#define CCL_WARPS 8
+
+// 1. per row: number of runs + per-word exclusive prefix of run starts
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_rowcount(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+               int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    const u32* m = mask + (size_t)f * d.NW;
+    CclBuf b = bufs[f];
+    int lane = lane_id();
+    int base = 0;
+    for (int w0 = 0; w0 < d.WW; w0 += 32) {
+        int w = w0 + lane;
+        u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
+        u32 starts = cur & ~((cur << 1) | (prev >> 31));
+        int c = __popc(starts);
+        int inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULLMASK, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (w < d.WW) b.wpre[(size_t)y * d.WW + w] = (u16)(base + inc - c);
+        base += __shfl_sync(FULLMASK, inc, 31);
+    }
+    if (lane == 0) b.rowcnt[y] = base;
+}
+
+// 2. exclusive scan of the row counts; one 1024-thread block per frame
+__global__ void __launch_bounds__(1024)
+k_ccl_rowscan(CclBuf* __restrict__ bufs, FrameCtl* __restrict__ ctl, int pass, Dims d, int kind, int maxruns)
+{
+    int f = blockIdx.x;
+    if (!ctl[f].active[pass]) return;
+    CclBuf b = bufs[f];
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int y0 = 0; y0 < d.H; y0 += 1024) {
+        int y = y0 + t;
+        int c = (y < d.H) ? b.rowcnt[y] : 0;
+        int inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULLMASK, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int s = wsum[lane], si = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(FULLMASK, si, o);
+                if (lane >= o) si += v;
+            }
+            wsum[lane] = si - s;
+        }
+        __syncthreads();
+        int excl = carry + wsum[wid] + inc - c;
+        if (y < d.H) b.rowbase[y] = excl;
+        __syncthreads();
+        if (t == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (t == 0) {
+        int total = carry;
+        b.rowbase[d.H] = total;
+        if (total > maxruns) {
+            atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
+            ctl[f].active[0] = ctl[f].active[1] = 0;     // drop the frame: later kernels skip it
+            total = 0;
+        }
+        ctl[f].nruns[kind] = total;
+    }
+}
+
+// 3. materialise runs: id = rowbase[y] + rank; parent = id
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_fill(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+           int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    const u32* m = mask + (size_t)f * d.NW;
+    CclBuf b = bufs[f];
+    int rb = b.rowbase[y];
+    for (int w = lane_id(); w < d.WW; w += 32) {
+        u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
+        u32 starts = cur & ~((cur << 1) | (prev >> 31));
+        int id = rb + b.wpre[(size_t)y * d.WW + w];
+        while (starts) {
+            int s = __ffs(starts) - 1;
+            starts &= starts - 1;
+            // end of the run: count the consecutive set bits from s upward (may continue in later words)
+            u32 above = ~(cur >> s);
+            int t = above ? (__ffs(above) - 1) : 32;       // s == 0 and an all-ones word
+            int xe;
+            if (s + t < 32) {
+                xe = (w << 5) + s + t - 1;
+            } else {
+                xe = (w << 5) + 31;
+                for (int w2 = w + 1; w2 < d.WW; w2++) {
+                    u32 nx = ~ccl_word(m, y, w2, d, kind);
+                    int t2 = nx ? (__ffs(nx) - 1) : 32;    // trailing ones of the next word
+                    xe = (w2 << 5) + t2 - 1;
+                    if (t2 < 32) break;
+                }
+            }
+            Run r; r.xs = (u16)((w << 5) + s); r.xe = (u16)xe; r.y = (u16)y; r.pad = 0;
+            b.runs[id] = r;
+            b.parent[id] = id;
+            b.flag[id] = 0;
+            b.ymax[id] = y;
+            b.compidx[id] = -1;
+            id++;
+        }
+    }
+}
+
+// index of the run of row y that contains pixel p (which must be set)
+__device__ __forceinline__ int run_at(const u32* __restrict__ m, const CclBuf& b, int y, int p, Dims d, int kind)
+{
+    int w = p >> 5, bit = p & 31;
+    u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
+    u32 starts = cur & ~((cur << 1) | (prev >> 31));
+    u32 upto = (bit == 31) ? 0xffffffffu : ((2u << bit) - 1u);
+    return b.rowbase[y] + b.wpre[(size_t)y * d.WW + w] + __popc(starts & upto) - 1;
+}
+
+// 4. union every run with the runs of the previous row it touches (8- or 4-connectivity)
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+            int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H || y == 0) return;
+    const u32* m = mask + (size_t)f * d.NW;
+    CclBuf b = bufs[f];
+    if (ctl[f].nruns[kind] == 0) return;
+    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+    const int c = kind ? 0 : 1;
+    for (int id = r0 + lane_id(); id < r1; id += 32) {
+        Run r = b.runs[id];
+        int lo = max((int)r.xs - c, 0), hi = min((int)r.xe + c, d.W - 1);
+        for (int w = lo >> 5; w <= (hi >> 5); w++) {
+            u32 up = ccl_word(m, y - 1, w, d, kind);
+            int blo = max(lo - (w << 5), 0), bhi = min(hi - (w << 5), 31);
+            u32 bits = up & bit_range(blo, bhi);
+            while (bits) {
+                int p = __ffs(bits) - 1;
+                int j = run_at(m, b, y - 1, (w << 5) + p, d, kind);
+                uf_union(b.parent, id, j);
+                // drop the rest of that run inside this word
+                u32 ones = ~up & (0xffffffffu << p);          // first clear bit at or above p
+                int e = ones ? (__ffs(ones) - 1) : 32;       // run covers bits p .. e-1
+                bits &= (e >= 32) ? 0u : (0xffffffffu << e);
+            }
+        }
+    }
+}
+
+// 5. flatten + per-component statistics at the root
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_stats(const u32* __restrict__ strong, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+            int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    if (ctl[f].nruns[kind] == 0) return;
+    const u32* sm = strong ? strong + (size_t)f * d.NW : nullptr;
+    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+    for (int id = r0 + lane_id(); id < r1; id += 32) {
+        Run r = b.runs[id];
+        int root = uf_find(b.parent, id);
+        b.parent[id] = root;
+        int fl = 0;
+        if (kind == 0) {
+            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                if (sm[(size_t)y * d.WW + w] & bit_range(blo, bhi)) { fl = 1; break; }
+            }
+        } else {
+            fl = (y == 0 || y == d.H - 1 || r.xs == 0 || r.xe == d.W - 1) ? 1 : 0;
+        }
+        if (fl) atomicOr(&b.flag[root], 1);
+        if (root != id) atomicMax(&b.ymax[root], y);
+    }
+}
+
+// 6. Canny output: edges = runs of candidate components that hold a strong pixel
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_edges(CclBuf* __restrict__ bufs, u32* __restrict__ edges, const FrameCtl* __restrict__ ctl, int pass, Dims d)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int wid = threadIdx.x >> 5;
+    int y = blockIdx.x * CCL_WARPS + wid;
+    __shared__ u32 row[CCL_WARPS][128];
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    for (int w = lane_id(); w < d.WW; w += 32) row[wid][w] = 0;
+    __syncwarp();
+    if (ctl[f].nruns[0] > 0) {
+        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+        for (int id = r0 + lane_id(); id < r1; id += 32) {
+            int root = b.parent[id];
+            if (!(b.flag[root] & 1)) continue;
+            Run r = b.runs[id];
+            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                atomicOr(&row[wid][w], bit_range(blo, bhi));
+            }
+        }
+    }
+    __syncwarp();
+    for (int w = lane_id(); w < d.WW; w += 32) edges[(size_t)f * d.NW + (size_t)y * d.WW + w] = row[wid][w];
+}
+
+// Contour bookkeeping, one entry per selected component.
+struct CompBuf {
+    int* root;        // [2*maxcomp]  fg entries first, then bg
+    int* y0;          // first row of the point set
+    int* h;           // rows
+    int* slot;        // offset into rowmin/rowmax
+    int* hulloff;     // offset into the hull scratch
+    int* rowmin;      // [slotcap]
+    int* rowmax;      // [slotcap]
+    int slotcap, hullcap, maxcomp;
+};
+
+// 7. allocate a contour for every selected root (fg: holds a strong pixel; bg: does not touch the border)
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_alloc(CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps, FrameCtl* __restrict__ ctl, int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    CompBuf cb = comps[f];
+    if (ctl[f].nruns[kind] == 0) return;
+    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+    for (int id = r0 + lane_id(); id < r1; id += 32) {
+        if (b.parent[id] != id) continue;
+        bool sel = kind == 0 ? (b.flag[id] & 1) : !(b.flag[id] & 1);
+        if (!sel) continue;
+        int ci = atomicAdd(&ctl[f].ncomp[kind], 1);
+        int hh = b.ymax[id] - y + 1 + (kind ? 2 : 0);
+        int slot = atomicAdd(&ctl[f].nslots[0], hh);
+        int ho = atomicAdd(&ctl[f].nhull[0], 2 * hh + 2);
+        if (ci >= cb.maxcomp || slot + hh > cb.slotcap || ho + 2 * hh + 2 > cb.hullcap) {
+            atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
+            continue;
+        }
+        int e = kind * cb.maxcomp + ci;
+        cb.root[e] = id;
+        cb.y0[e] = y - (kind ? 1 : 0);
+        cb.h[e] = hh;
+        cb.slot[e] = slot;
+        cb.hulloff[e] = ho;
+        for (int i = 0; i < hh; i++) { cb.rowmin[slot + i] = 0x7fffffff; cb.rowmax[slot + i] = -1; }
+        b.compidx[id] = e;
+    }
+}
+
+// 8. per-row extremes of every contour's point set
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_extremes(const u32* __restrict__ edges, CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps,
+               const FrameCtl* __restrict__ ctl, int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    CompBuf cb = comps[f];
+    if (ctl[f].nruns[kind] == 0) return;
+    const u32* em = edges + (size_t)f * d.NW;
+    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+    for (int id = r0 + lane_id(); id < r1; id += 32) {
+        int e = b.compidx[b.parent[id]];
+        if (e < 0) continue;
+        Run r = b.runs[id];
+        int s = cb.slot[e] + (y - cb.y0[e]);
+        if (kind == 0) {
+            atomicMin(&cb.rowmin[s], (int)r.xs);
+            atomicMax(&cb.rowmax[s], (int)r.xe);
+        } else {
+            // hole run [xs, xe] on row y (never on the frame border): edge pixels 4-adjacent to it
+            atomicMin(&cb.rowmin[s], (int)r.xs - 1);
+            atomicMax(&cb.rowmax[s], (int)r.xe + 1);
+            for (int dy = -1; dy <= 1; dy += 2) {
+                int yy = y + dy;
+                int first = -1, last = -1;
+                for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                    int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                    u32 bits = em[(size_t)yy * d.WW + w] & bit_range(blo, bhi);
+                    if (bits) {
+                        if (first < 0) first = (w << 5) + __ffs(bits) - 1;
+                        last = (w << 5) + 31 - __clz(bits);
+                    }
+                }
+                if (first >= 0) {
+                    atomicMin(&cb.rowmin[s + dy], first);
+                    atomicMax(&cb.rowmax[s + dy], last);
+                }
+            }
+        }
+    }
+}
+
+// labels tap: int32 per pixel = raster-first pixel index of the component (fg) / hole (bg)
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_labels(CclBuf* __restrict__ bufs, int* __restrict__ labels, const FrameCtl* __restrict__ ctl, int pass,
+             Dims d, int kind, int frame)
+{
+    int f = frame;
+    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    int* out = labels + (size_t)y * d.W;
+    for (int x = lane_id(); x < d.W; x += 32) out[x] = -1;
+    __syncwarp();
+    if (ctl[f].nruns[kind] == 0) return;
+    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+    for (int id = r0 + lane_id(); id < r1; id += 32) {
+        int root = b.parent[id];
+        Run r = b.runs[id], rr = b.runs[root];
+        int lab;
+        if (kind == 0) lab = (b.flag[root] & 1) ? (int)rr.y * d.W + (int)rr.xs : -1;
+        else lab = (b.flag[root] & 1) ? -2 : (int)rr.y * d.W + (int)rr.xs;
+        for (int x = r.xs; x <= r.xe; x++) out[x] = lab;
+    }
+}

@@ -1,0 +1,275 @@
+// k_hough.cuh - cv2.HoughLines-compatible standard Hough transform on bit masks, plus the line-set check.
+//
+// Reference calls (paths under /root/reference/lfd/detecttrails/):
+//   processfield.py:370-371, :488-489   cv2.HoughLines(equ | box_img, houghMethod, np.pi/180, 1)
+//   processfield.py:36-150              check_theta
+// cv2 semantics (restated and pinned in oracle/c/cvrestate.c::orc_hough_lines): every NON-ZERO pixel votes
+// r = cvRound(x*tabCos[n] + y*tabSin[n]) + (numrho-1)/2 with float32 tables (sin/cos in double, divided by
+// rho, rounded to float; built on the host exactly as OpenCV does), separate roundings for both products
+// and the sum (no FMA), round-half-even.  Peaks: votes > threshold, 4-neighbour maximum with OpenCV's
+// > / >= asymmetry, sorted by (votes desc, accumulator index asc).
+//
+// Design: the voting unit is a non-zero 32-pixel mask word, not a pixel.  For one angle the 32 pixels of
+// a word span at most ceil(32*|cos|/rho)+1 rho bins, so a lane (= angle) usually issues ONE shared-memory
+// atomic of weight popc(word) instead of 32.  Accumulators are privatised per CTA in shared memory as
+// int32 [angles-per-CTA][numrho+2] and flushed once with global atomics.
+#pragma once
+#include "common.cuh"
+
+// non-zero words of the equ mask (which=0) and box mask (which=1) -> (y<<16 | w, bits)
+__global__ void __launch_bounds__(256)
+k_hough_compact(const u32* __restrict__ nzmask, const u32* __restrict__ boxmask, uint2* __restrict__ segs,
+                FrameCtl* __restrict__ ctl, int pass, Dims d, size_t seg_stride)
+{
+    int f = blockIdx.y, which = blockIdx.z;
+    if (!ctl[f].active[pass] || !ctl[f].hough[pass]) return;
+    const u32* m = (which ? boxmask : nzmask) + (size_t)f * d.NW;
+    uint2* out = segs + ((size_t)f * 2 + which) * seg_stride;
+    int lane = lane_id();
+    int nnz = 0;
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < d.NW; i0 += gridDim.x * blockDim.x) {
+        int i = i0 + lane;
+        u32 v = (i < d.NW) ? m[i] : 0u;
+        u32 bal = __ballot_sync(FULLMASK, v != 0);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ctl[f].nseg[which], __popc(bal));
+            base = __shfl_sync(FULLMASK, base, 0);
+            if (v) {
+                int y = i / d.WW, w = i - y * d.WW;
+                out[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(((u32)y << 16) | (u32)w, v);
+                nnz += __popc(v);
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) nnz += __shfl_xor_sync(FULLMASK, nnz, o);
+    if (lane == 0 && nnz) atomicAdd(&ctl[f].nnz[which], nnz);
+}
+
+#define HOUGH_THREADS 256
+
+// grid = (chunks, ngroups, 2*n); dynamic smem = apc * RS * 4 bytes
+__global__ void __launch_bounds__(HOUGH_THREADS)
+k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const float* __restrict__ tabSin,
+             const float* __restrict__ tabCos, const FrameCtl* __restrict__ ctl, int pass, HoughCfg hc,
+             size_t seg_stride, size_t accum_stride)
+{
+    extern __shared__ int acc[];
+    int f = blockIdx.z >> 1, which = blockIdx.z & 1;
+    if (!ctl[f].active[pass] || !ctl[f].hough[pass]) return;
+    int nseg = ctl[f].nseg[which];
+    int g = blockIdx.y;
+    int a0 = g * hc.apc;
+    int na = min(hc.apc, hc.numangle - a0);
+    for (int i = threadIdx.x; i < hc.apc * hc.RS; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const uint2* sg = segs + ((size_t)f * 2 + which) * seg_stride;
+    int lane = lane_id();
+    // lanes = angles; when apc < 32 the warp covers 32/apc segments at once
+    int per = (hc.apc >= 32) ? 1 : (32 / hc.apc);
+    int sub = lane / hc.apc, a = lane - sub * hc.apc;
+    bool live = (per == 1) ? (lane < na) : (sub < per && a < na);
+    if (per == 1) { sub = 0; a = lane; }
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float c = 0.f, s = 0.f;
+    if (live) { c = tabCos[a0 + a]; s = tabSin[a0 + a]; }
+    const int off = (hc.numrho - 1) / 2 + 1;
+    int* row = acc + a * hc.RS + off;
+    for (int si = warp * per; si < nseg; si += nwarps * per) {
+        int idx = si + sub;
+        if (!live || idx >= nseg) continue;
+        uint2 sgv = sg[idx];
+        int y = sgv.x >> 16, x0 = (sgv.x & 0xffff) << 5;
+        u32 m = sgv.y;
+        float ys = __fmul_rn((float)y, s);
+        int fb = __ffs(m) - 1, lb = 31 - __clz(m);
+        int r1 = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + fb), c), ys));
+        int r2 = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + lb), c), ys));
+        if (r1 == r2) {
+            atomicAdd(&row[r1], __popc(m));
+        } else {
+            int cur = r1, cnt = 1;
+            m &= m - 1;
+            while (m) {
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                int r = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + b), c), ys));
+                if (r == cur) cnt++;
+                else { atomicAdd(&row[cur], cnt); cur = r; cnt = 1; }
+            }
+            atomicAdd(&row[cur], cnt);
+        }
+    }
+    __syncthreads();
+    int* gacc = accum + ((size_t)f * 2 + which) * accum_stride;
+    for (int i = threadIdx.x; i < na * hc.RS; i += blockDim.x) {
+        int v = acc[i];
+        if (v) {
+            int aa = i / hc.RS, col = i - aa * hc.RS;
+            atomicAdd(&gacc[(size_t)(a0 + aa + 1) * hc.RS + col], v);
+        }
+    }
+}
+
+// peaks -> 64-bit sort keys ((INT_MAX - votes) << 32 | accumulator index): ascending key order is
+// OpenCV's (votes desc, index asc)
+__global__ void __launch_bounds__(256)
+k_hough_peaks(const int* __restrict__ accum, u64* __restrict__ keys, FrameCtl* __restrict__ ctl, int pass,
+              HoughCfg hc, size_t accum_stride, size_t key_stride)
+{
+    int f = blockIdx.y >> 1, which = blockIdx.y & 1;
+    if (!ctl[f].active[pass] || !ctl[f].hough[pass]) return;
+    const int* A = accum + ((size_t)f * 2 + which) * accum_stride;
+    u64* K = keys + ((size_t)f * 2 + which) * key_stride;
+    int cells = hc.numangle * hc.numrho;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+        int n = i / hc.numrho, r = i - n * hc.numrho;
+        int base = (n + 1) * hc.RS + r + 1;
+        int v = A[base];
+        if (v > hc.threshold && v > A[base - 1] && v >= A[base + 1] && v > A[base - hc.RS] && v >= A[base + hc.RS]) {
+            int pos = atomicAdd(&ctl[f].npeaks[which], 1);
+            K[pos] = ((u64)(u32)(0x7fffffff - v) << 32) | (u32)base;
+        }
+    }
+}
+
+__device__ __forceinline__ void key_to_line(u64 key, const HoughCfg& hc, float* rho, float* theta)
+{
+    int base = (int)(key & 0xffffffffu);
+    int n = base / hc.RS - 1;
+    int r = base - (n + 1) * hc.RS - 1;
+    *rho = __fmul_rn((float)(r - (hc.numrho - 1) / 2), hc.rho);
+    *theta = __fmul_rn((float)n, hc.theta);
+}
+
+// first K lines in OpenCV order without a full sort: K rounds of block-wide minimum over the keys.
+// grid = (2, n); writes lfd_result.top_equ / top_box and n_lines_*.
+__global__ void __launch_bounds__(256)
+k_hough_topk(const u64* __restrict__ keys, lfd_result* __restrict__ res, const FrameCtl* __restrict__ ctl,
+             int pass, HoughCfg hc, size_t key_stride, int K)
+{
+    int which = blockIdx.x, f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    lfd_result* R = res + f;
+    if (!ctl[f].hough[pass]) {
+        if (threadIdx.x == 0) { if (which) R->n_lines_box[pass] = -1; else R->n_lines_equ[pass] = -1; }
+        return;
+    }
+    const u64* Kk = keys + ((size_t)f * 2 + which) * key_stride;
+    int np = ctl[f].npeaks[which];
+    __shared__ u64 sm[256];
+    __shared__ u64 prev_s;
+    u64 prev = 0;
+    bool have_prev = false;
+    for (int k = 0; k < K; k++) {
+        u64 best = ~0ull;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            u64 v = Kk[i];
+            if ((!have_prev || v > prev) && v < best) best = v;
+        }
+        sm[threadIdx.x] = best;
+        __syncthreads();
+        for (int o = 128; o; o >>= 1) {
+            if (threadIdx.x < o) { u64 b = sm[threadIdx.x + o]; if (b < sm[threadIdx.x]) sm[threadIdx.x] = b; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            prev_s = sm[0];
+            float* dst = which ? R->top_box[pass][k] : R->top_equ[pass][k];
+            if (sm[0] != ~0ull) key_to_line(sm[0], hc, &dst[0], &dst[1]);
+            else { dst[0] = 0.f; dst[1] = 0.f; }
+        }
+        __syncthreads();
+        prev = prev_s;
+        have_prev = true;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { if (which) R->n_lines_box[pass] = np; else R->n_lines_equ[pass] = np; }
+}
+
+// full sort (taps / lfd_hough_lines): bitonic sort of the keys in global memory by one CTA,
+// then (rho, theta) for every line.  key buffer must have room for next_pow2(npeaks).
+__global__ void __launch_bounds__(1024)
+k_hough_sort(u64* __restrict__ keys, float* __restrict__ lines, const FrameCtl* __restrict__ ctl, int pass,
+             HoughCfg hc, size_t key_stride, size_t line_stride, int max_lines)
+{
+    int which = blockIdx.x, f = blockIdx.y;
+    if (!ctl[f].active[pass] || !ctl[f].hough[pass]) return;
+    u64* Kk = keys + ((size_t)f * 2 + which) * key_stride;
+    int np = ctl[f].npeaks[which];
+    int n2 = 1;
+    while (n2 < np) n2 <<= 1;
+    for (int i = np + threadIdx.x; i < n2; i += blockDim.x) Kk[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    u64 a = Kk[i], b = Kk[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { Kk[i] = b; Kk[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    float* L = lines + ((size_t)f * 2 + which) * line_stride;
+    for (int i = threadIdx.x; i < np && i < max_lines; i += blockDim.x) key_to_line(Kk[i], hc, &L[2 * i], &L[2 * i + 1]);
+}
+
+// check_theta (processfield.py:36-150) + the pass verdict; one thread per frame.
+// float64 arithmetic on float32-valued inputs like the NumPy original; a short second set leaves
+// theta1[i] at 0 as well (the four assignments share one try block, :93-102).
+__global__ void k_check_theta(lfd_result* __restrict__ res, FrameCtl* __restrict__ ctl, int pass, int n,
+                              int navg, double dro, double thetaTresh, double lineSetTresh)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    lfd_result* R = res + f;
+    if (!ctl[f].active[pass]) return;
+    R->rect_detection[pass] = ctl[f].hough[pass];
+    bool detected = false;
+    if (ctl[f].hough[pass]) {
+        int n1 = R->n_lines_equ[pass], n2 = R->n_lines_box[pass];
+        if (n1 <= 0) atomicOr(&ctl[f].status, LFD_FRAME_NO_LINES_EQU);
+        if (n2 <= 0) atomicOr(&ctl[f].status, LFD_FRAME_NO_LINES_BOX);
+        if (n1 > 0 && n2 > 0) {
+            double ro1[LFD_MAX_SET_LINES], ro2[LFD_MAX_SET_LINES], t1[LFD_MAX_SET_LINES], t2[LFD_MAX_SET_LINES];
+            for (int i = 0; i < navg; i++) {
+                ro1[i] = ro2[i] = t1[i] = t2[i] = 0.0;
+                if (i < n1) {
+                    ro1[i] = (double)R->top_equ[pass][i][0];
+                    if (i < n2) {
+                        ro2[i] = (double)R->top_box[pass][i][0];
+                        t1[i] = (double)R->top_equ[pass][i][1];
+                        t2[i] = (double)R->top_box[pass][i][1];
+                    }
+                }
+            }
+            double s1 = 0, s2 = 0, mx1 = t1[0], mn1 = t1[0], mx2 = t2[0], mn2 = t2[0], sd = 0;
+            for (int i = 0; i < navg; i++) {
+                s1 += ro1[i]; s2 += ro2[i];
+                mx1 = fmax(mx1, t1[i]); mn1 = fmin(mn1, t1[i]);
+                mx2 = fmax(mx2, t2[i]); mn2 = fmin(mn2, t2[i]);
+                sd += fabs(t1[i] - t2[i]);
+            }
+            bool reject = false;
+            if (fabs(s1 / navg - s2 / navg) > dro) reject = true;
+            else if (fabs(mx1 - mn1) > thetaTresh) reject = true;
+            else if (fabs(mx2 - mn2) > thetaTresh) reject = true;
+            else if (sd / navg > lineSetTresh) reject = true;
+            R->rejected[pass] = reject ? 1 : 0;
+            detected = !reject;
+        }
+    }
+    if (detected) {
+        R->detected = 1;
+        R->pass = pass;
+        R->rho = R->top_equ[pass][0][0];
+        R->theta = R->top_equ[pass][0][1];
+    }
+    R->status = ctl[f].status;
+    // the dim pass only runs when bright did not detect (detecttrails.py:126-129)
+    if (pass == 0) ctl[f].active[1] = (detected || (ctl[f].status & (LFD_FRAME_NO_LINES_EQU | LFD_FRAME_NO_LINES_BOX | LFD_FRAME_OVERFLOW))) ? 0 : ctl[f].active[1];
+}

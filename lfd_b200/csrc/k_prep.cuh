@@ -1,0 +1,173 @@
+// k_prep.cuh - star mask rasterisation, fused blot+flip+clip+convertScaleAbs+histogram, equalisation LUT.
+//
+// Reference behaviour (paths under /root/reference/lfd/detecttrails/):
+//   removestars.py:231      img[x-dxy:x+dxy, y-dxy:y+dxy].fill(0.0)  -> k_star_mask (+ applied in k_prep)
+//   detecttrails.py:124     cv2.flip(img, 0)                          -> source row H-1-y in k_prep
+//   processfield.py:342     img[img < 0] = 0                          -> bright clip
+//   processfield.py:453-454 img[img < minFlux] = 0; img[img > 0] += addFlux
+//   processfield.py:346,456 cv2.convertScaleAbs                       -> csa()
+//   processfield.py:347,457 cv2.equalizeHist                          -> histogram here, LUT in k_lut
+#pragma once
+#include "common.cuh"
+
+// rects: (r0, r1, c0, c1) half-open on the UN-flipped image, per frame via rect_off.
+// mask: [n][H][WW] bit per pixel in the FLIPPED orientation (row H-1-r).
+__global__ void k_star_mask(const int4* __restrict__ rects, const int* __restrict__ rect_off,
+                            u32* __restrict__ mask, Dims d)
+{
+    int f = blockIdx.y;
+    int nr = rect_off[f + 1] - rect_off[f];
+    int ri = blockIdx.x;
+    if (ri >= nr) return;
+    int4 r = rects[rect_off[f] + ri];
+    int r0 = max(r.x, 0), r1 = min(r.y, d.H), c0 = max(r.z, 0), c1 = min(r.w, d.W);
+    if (r0 >= r1 || c0 >= c1) return;
+    int w0 = c0 >> 5, w1 = (c1 - 1) >> 5;
+    int nw = w1 - w0 + 1;
+    int total = (r1 - r0) * nw;
+    u32* m = mask + (size_t)f * d.NW;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int row = r0 + i / nw, w = w0 + i % nw;
+        int lo = max(c0 - (w << 5), 0), hi = min(c1 - 1 - (w << 5), 31);
+        atomicOr(&m[(size_t)(d.H - 1 - row) * d.WW + w], bit_range(lo, hi));
+    }
+}
+
+// cv2.convertScaleAbs for alpha=1, beta=0: saturate_u8(rint(|v|)); NaN, inf and |v| >= 2^31 give 0
+// (x86 cvtps2dq "integer indefinite" is negative and saturates to 0).
+__device__ __forceinline__ u32 csa(float v)
+{
+    float a = fabsf(v);
+    if (!(a < 2147483648.0f)) return 0u;
+    int r = __float2int_rn(a);
+    return (u32)min(r, 255);
+}
+
+__device__ __forceinline__ float bswapf(float v)
+{
+    return __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123));
+}
+
+// mode 0: whole-frame pipeline: mask + flip + bright clip -> gray0 ; + dim threshold/offset -> gray1
+// mode 1: standalone bright on an already flipped frame (no mask, no flip) -> gray0
+// mode 2: standalone dim on an already flipped frame (no bright clip)     -> gray1
+// Each thread converts 4 consecutive pixels (W % 4 == 0).  hist: [2][n][256].
+// clipped (optional): float image after the in-place clip of the selected standalone pass.
+__global__ void __launch_bounds__(256)
+k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0,
+       u8* __restrict__ gray1, u32* __restrict__ hist0, u32* __restrict__ hist1, float* __restrict__ clipped,
+       Dims d, int mode, int bigendian, float minFlux, float addFlux)
+{
+    __shared__ u32 sh[2][256];
+    int f = blockIdx.y;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+
+    const float* src = in + (size_t)f * d.N;
+    int quads = d.N >> 2;
+    int wq = d.W >> 2;
+    u32 zeros0 = 0, zeros1 = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+        int y = q / wq, x = (q - y * wq) << 2;
+        int sy = (mode == 0) ? (d.H - 1 - y) : y;
+        float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)sy * d.W + x));
+        if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+        float a[4] = {v.x, v.y, v.z, v.w};
+        u32 mbits = 0;
+        if (mode == 0) mbits = (mask[(size_t)f * d.NW + (size_t)y * d.WW + (x >> 5)] >> (x & 31)) & 0xf;
+        u32 g0 = 0, g1 = 0;
+        float cl[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float t = a[k];
+            if (mbits & (1u << k)) t = 0.0f;
+            if (mode != 2) { if (t < 0.0f) t = 0.0f; }          // bright clip (NaN stays NaN)
+            float b = t;
+            if (mode != 1) {
+                if (b < minFlux) b = 0.0f;
+                if (b > 0.0f) b = __fadd_rn(b, addFlux);
+            }
+            u32 c0 = csa(t), c1 = csa(b);
+            g0 |= c0 << (8 * k);
+            g1 |= c1 << (8 * k);
+            if (mode != 2) { if (c0) atomicAdd(&sh[0][c0], 1u); else zeros0++; }
+            if (mode != 1) { if (c1) atomicAdd(&sh[1][c1], 1u); else zeros1++; }
+            cl[k] = (mode == 2) ? b : t;
+        }
+        size_t o = (size_t)f * d.N + (size_t)y * d.W + x;
+        if (mode != 2) *reinterpret_cast<u32*>(gray0 + o) = g0;
+        if (mode != 1) *reinterpret_cast<u32*>(gray1 + o) = g1;
+        if (clipped) *reinterpret_cast<float4*>(clipped + o) = make_float4(cl[0], cl[1], cl[2], cl[3]);
+    }
+    // zero bin: warp-aggregate the dominant value before touching shared memory
+    for (int o = 16; o; o >>= 1) {
+        zeros0 += __shfl_xor_sync(FULLMASK, zeros0, o);
+        zeros1 += __shfl_xor_sync(FULLMASK, zeros1, o);
+    }
+    if (lane_id() == 0) {
+        if (zeros0) atomicAdd(&sh[0][0], zeros0);
+        if (zeros1) atomicAdd(&sh[1][0], zeros1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        if (mode != 2 && sh[0][i]) atomicAdd(&hist0[(size_t)f * 256 + i], sh[0][i]);
+        if (mode != 1 && sh[1][i]) atomicAdd(&hist1[(size_t)f * 256 + i], sh[1][i]);
+    }
+}
+
+// cv2.equalizeHist's LUT from the 256-bin histogram; one 256-thread block per (frame, pass).
+// grid = (n, 2): blockIdx.y selects hist/lut of pass 0/1 (pointers are [2][n][256] slabs).
+__global__ void __launch_bounds__(256)
+k_lut(const u32* __restrict__ hist, u8* __restrict__ lut, const FrameCtl* __restrict__ ctl, int n, int total,
+      int pass_lo)
+{
+    int f = blockIdx.x, p = pass_lo + blockIdx.y;
+    if (!ctl[f].active[p]) return;
+    const u32* h = hist + ((size_t)p * n + f) * 256;
+    u8* l = lut + ((size_t)p * n + f) * 256;
+    __shared__ int s[256];
+    __shared__ int i0s;
+    int t = threadIdx.x;
+    int hv = (int)h[t];
+    if (t == 0) i0s = 256;
+    __syncthreads();
+    if (hv > 0) atomicMin(&i0s, t);
+    __syncthreads();
+    int i0 = i0s;
+    if (i0 == 256 || (int)h[i0] == total) { l[t] = (u8)t; return; }   // constant image: dst = src
+    s[t] = (t > i0) ? hv : 0;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        int v = (t >= o) ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    float scale = 255.0f / (float)(total - (int)h[i0]);
+    int val = 0;
+    if (t > i0) {
+        val = __float2int_rn(__fmul_rn((float)s[t], scale));
+        val = min(max(val, 0), 255);
+    }
+    l[t] = (u8)val;
+}
+
+// expand a bit mask to a 0/255 uint8 plane (stage taps)
+__global__ void k_expand_mask(const u32* __restrict__ mask, u8* __restrict__ out, Dims d)
+{
+    int f = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+        int y = i / d.W, x = i - y * d.W;
+        u32 w = mask[(size_t)f * d.NW + (size_t)y * d.WW + (x >> 5)];
+        out[(size_t)f * d.N + i] = ((w >> (x & 31)) & 1u) ? 255 : 0;
+    }
+}
+
+// LUT applied to a plane (EQU tap: equalizeHist output before morphology)
+__global__ void k_apply_lut(const u8* __restrict__ in, const u8* __restrict__ lut, u8* __restrict__ out, Dims d)
+{
+    int f = blockIdx.y;
+    const u8* l = lut + (size_t)f * 256;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x)
+        out[(size_t)f * d.N + i] = l[in[(size_t)f * d.N + i]];
+}

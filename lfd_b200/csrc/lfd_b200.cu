@@ -1,0 +1,890 @@
+// lfd_b200.cu - handle, device memory layout, pipeline orchestration and the C ABI of include/lfd_b200.h.
+//
+// One handle = one GPU, one stream, buffers for `max_batch` frames.  A batch goes through
+//   star mask -> prep (blot+flip+clip+u8+hist, both passes in one read of the float frame)
+//   per pass: LUT -> morphology -> Sobel/NMS -> run-CCL (hysteresis + outer contours) -> run-CCL of the
+//   background (hole contours) -> minAreaRect/filter/boxPoints -> box fill -> Hough x2 -> check_theta
+// with every kernel gridded over (work, frame); frames a pass does not apply to exit at the first line
+// (bright detected -> no dim; no rectangle passed -> no Hough), so there is no host round trip inside a batch.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "geom.cuh"
+#include "k_canny.cuh"
+#include "k_ccl.cuh"
+#include "k_hough.cuh"
+#include "k_morph.cuh"
+#include "k_prep.cuh"
+#include "k_rects.cuh"
+
+static std::string g_create_error;
+
+enum { T_PREP = 0, T_MORPH, T_CANNY, T_CCL_FG, T_CCL_BG, T_RECTS, T_HOUGH, T_CHECK, T_PER_PASS };
+static const char* k_timing_names[] = {
+    "prep(mask+flip+clip+u8+hist)",
+    "bright:lut+morph", "bright:sobel+nms", "bright:ccl_fg(hysteresis)", "bright:ccl_bg(holes)",
+    "bright:rects+boxfill", "bright:hough", "bright:check_theta",
+    "dim:lut+morph", "dim:sobel+nms", "dim:ccl_fg(hysteresis)", "dim:ccl_bg(holes)",
+    "dim:rects+boxfill", "dim:hough", "dim:check_theta",
+    "results_d2h"};
+#define N_TIMINGS 16
+
+struct HoughBufs {
+    HoughCfg hc;
+    float* tabSin = nullptr;   // device
+    float* tabCos = nullptr;
+    size_t accum_stride = 0, key_stride = 0, line_stride = 0;
+    int max_lines = 0;
+    int* accum = nullptr;      // [B][2][accum_stride]
+    u64* keys = nullptr;       // [B][2][key_stride]
+    float* lines = nullptr;    // [B][2][line_stride]  (allocated on first FULL_LINES use)
+    size_t smem = 0;
+};
+
+struct lfd_handle {
+    int device = 0, B = 0;
+    Dims d;
+    lfd_config cfg;
+    lfd_params params;
+    bool have_params = false;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int last_n = 0, last_flags = 0;
+    bool pending = false;
+
+    // device
+    float* in = nullptr;              // [B][N]
+    u32* starmask = nullptr;          // [B][NW]
+    int4* rects_d = nullptr;          // [B*max_star_rects]
+    int* rect_off_d = nullptr;        // [B+1]
+    u8* gray[2] = {nullptr, nullptr}; // [B][N]
+    u32* hist = nullptr;              // [2][B][256]
+    u8* lut = nullptr;                // [2][B][256]
+    u8* morph[2] = {nullptr, nullptr};
+    u32* nz[2] = {nullptr, nullptr};  // [B][NW]
+    u32* cand[2] = {nullptr, nullptr};
+    u32* strong[2] = {nullptr, nullptr};
+    u32* edges[2] = {nullptr, nullptr};
+    u32* box[2] = {nullptr, nullptr};
+    u8* tap_u8 = nullptr;             // [N] scratch for expanded taps
+    u8* eroded_tap = nullptr;         // [B][N] lazily
+    u8* nms_tap[2] = {nullptr, nullptr};
+    float* clipped = nullptr;         // [N] lazily (run_pass writeback)
+    int* labels_tap = nullptr;        // [N] lazily
+    FrameCtl* ctl = nullptr;          // [B]
+    lfd_result* res_d = nullptr;      // [B]
+    int64_t* counters_d = nullptr;    // [16]
+    uint2* segs = nullptr;            // [B][2][NW]
+    CclBuf* ccl_d[2] = {nullptr, nullptr};   // [B] per kind
+    CompBuf* comp_d = nullptr;               // [B]
+    RectBuf* rbuf_d[2] = {nullptr, nullptr}; // [B] per pass
+    std::vector<CclBuf> ccl_h[2];
+    std::vector<CompBuf> comp_h;
+    std::vector<RectBuf> rbuf_h[2];
+    std::vector<void*> allocs;
+    HoughBufs hb[2];
+
+    // host
+    float* frames_h = nullptr;        // pinned [B][N]
+    lfd_result* res_h = nullptr;      // pinned [B]
+    int4* rects_h = nullptr;          // pinned
+    int* rect_off_h = nullptr;        // pinned
+    FrameCtl* ctl_h = nullptr;        // pinned [B]
+    int64_t counters_h[16];
+
+    cudaEvent_t ev[N_TIMINGS + 1];
+    bool ev_valid[N_TIMINGS + 1];
+    float timings[N_TIMINGS];
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return LFD_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                             \
+    do {                                                                                           \
+        h->launches++;                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " at line " + std::to_string(__LINE__); \
+            return LFD_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(lfd_handle* h, T** p, size_t count)
+{
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return LFD_OK;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------
+// small bookkeeping kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ctl_init(FrameCtl* ctl, lfd_result* res, int n, int act0, int act1)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    FrameCtl c;
+    memset(&c, 0, sizeof(c));
+    c.active[0] = act0; c.active[1] = act1;
+    ctl[f] = c;
+    lfd_result r;
+    memset(&r, 0, sizeof(r));
+    r.pass = -1;
+    for (int p = 0; p < 2; p++) { r.rect_detection[p] = -1; r.n_lines_equ[p] = -1; r.n_lines_box[p] = -1; }
+    res[f] = r;
+}
+
+__global__ void k_pass_begin(FrameCtl* ctl, int n)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    FrameCtl* c = ctl + f;
+    c->nruns[0] = c->nruns[1] = 0; c->ncomp[0] = c->ncomp[1] = 0;
+    c->nslots[0] = c->nslots[1] = 0; c->nhull[0] = c->nhull[1] = 0;
+    c->npass = 0; c->nseg[0] = c->nseg[1] = 0; c->npeaks[0] = c->npeaks[1] = 0; c->nnz[0] = c->nnz[1] = 0;
+}
+
+__global__ void k_pass_end(FrameCtl* ctl, int n, int pass, int numangle, unsigned long long* counters)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    FrameCtl* c = ctl + f;
+    if (!c->active[pass]) return;
+    c->ncomp_saved[pass][0] = c->ncomp[0]; c->ncomp_saved[pass][1] = c->ncomp[1];
+    atomicAdd(&counters[0], (unsigned long long)c->nnz[0]);
+    atomicAdd(&counters[1], (unsigned long long)c->nnz[1]);
+    atomicAdd(&counters[2], (unsigned long long)(c->nnz[0] + c->nnz[1]) * numangle);
+    atomicAdd(&counters[3], (unsigned long long)c->nruns[0]);
+    atomicAdd(&counters[4], (unsigned long long)c->nruns[1]);
+    atomicAdd(&counters[5], (unsigned long long)(c->ncomp[0] + c->ncomp[1]));
+    atomicAdd(&counters[6], (unsigned long long)c->npass);
+    if (pass == 1) atomicAdd(&counters[7], 1ull);
+    if (c->hough[pass]) atomicAdd(&counters[8], 1ull);
+    atomicAdd(&counters[9 + pass], 1ull);
+}
+
+__global__ void k_pack_mask(const u8* __restrict__ img, u32* __restrict__ mask, Dims d)
+{
+    // one warp per 32 pixels
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = gw; i < d.NW; i += nwarps) {
+        int y = i / d.WW, w = i - y * d.WW;
+        int x = (w << 5) + lane;
+        bool nzp = x < d.W && img[(size_t)y * d.W + x] != 0;
+        u32 b = __ballot_sync(FULLMASK, nzp);
+        if (lane == 0) mask[i] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hough configuration (host): OpenCV's numangle/numrho and float trig tables
+// ------------------------------------------------------------------------------------------------
+static void hough_dims_host(int H, int W, double rho_, double theta_, int* numangle, int* numrho)
+{
+    float rho = (float)rho_, theta = (float)theta_;
+    int max_rho = W + H, min_rho = -max_rho;
+    double min_theta = 0, max_theta = M_PI;
+    int na = (int)floor((max_theta - min_theta) / theta) + 1;
+    if (na > 1 && fabs(M_PI - (na - 1) * theta) < theta / 2) --na;
+    *numangle = na;
+    *numrho = (int)lrint(((max_rho - min_rho) + 1) / rho);
+}
+
+static int hough_setup(lfd_handle* h, HoughBufs* hb, int H, int W, double rho_, double theta_, int threshold,
+                       int nframes, bool want_lines, int max_lines_cfg)
+{
+    if (!(rho_ > 0) || !(theta_ > 0)) { h->err = "HoughLines: rho and theta must be positive"; return LFD_E_ARG; }
+    HoughCfg hc;
+    hough_dims_host(H, W, rho_, theta_, &hc.numangle, &hc.numrho);
+    if (hc.numangle < 1 || hc.numrho < 1 || (double)hc.numangle * hc.numrho > 2.0e8) {
+        h->err = "HoughLines: accumulator size out of range";
+        return LFD_E_ARG;
+    }
+    hc.RS = hc.numrho + 2;
+    hc.rho = (float)rho_;
+    hc.theta = (float)theta_;
+    hc.threshold = threshold;
+    const size_t smem_budget = 96 * 1024;
+    int apc = (int)(smem_budget / ((size_t)hc.RS * 4));
+    if (apc > 32) apc = 32;
+    if (apc < 1) { h->err = "HoughLines: rho too fine for the shared-memory accumulator (numrho too large)"; return LFD_E_UNSUPPORTED; }
+    if (apc < 32) { int p = 1; while (p * 2 <= apc) p *= 2; apc = p; }   // power of two so sub-warps tile a warp
+    if (apc > hc.numangle) apc = hc.numangle < 32 ? next_pow2(hc.numangle) : 32;
+    hc.apc = apc;
+    hc.ngroups = (hc.numangle + apc - 1) / apc;
+    hb->smem = (size_t)apc * hc.RS * 4;
+    hb->hc = hc;
+    // tables, exactly as OpenCV builds them (float accumulation of the angle)
+    std::vector<float> ts(hc.numangle), tc(hc.numangle);
+    float irho = 1 / hc.rho;
+    float ang = 0.f;
+    for (int n = 0; n < hc.numangle; ang += hc.theta, n++) {
+        ts[n] = (float)(sin((double)ang) * irho);
+        tc[n] = (float)(cos((double)ang) * irho);
+    }
+    size_t accum_stride = (size_t)(hc.numangle + 2) * hc.RS;
+    size_t cells = (size_t)hc.numangle * hc.numrho;
+    size_t key_stride = (size_t)next_pow2((int)cells);
+    bool realloc_needed = (accum_stride != hb->accum_stride) || (key_stride != hb->key_stride) || !hb->accum;
+    if (realloc_needed) {
+        if (hb->accum) cudaFree(hb->accum);
+        if (hb->keys) cudaFree(hb->keys);
+        if (hb->lines) cudaFree(hb->lines);
+        if (hb->tabSin) cudaFree(hb->tabSin);
+        hb->accum = nullptr; hb->keys = nullptr; hb->lines = nullptr; hb->tabSin = nullptr;
+        CK(cudaMalloc((void**)&hb->accum, (size_t)nframes * 2 * accum_stride * sizeof(int)));
+        CK(cudaMalloc((void**)&hb->keys, (size_t)nframes * 2 * key_stride * sizeof(u64)));
+        CK(cudaMalloc((void**)&hb->tabSin, (size_t)2 * hc.numangle * sizeof(float)));
+        hb->tabCos = hb->tabSin + hc.numangle;
+        hb->accum_stride = accum_stride;
+        hb->key_stride = key_stride;
+    }
+    hb->max_lines = (max_lines_cfg > 0 && (size_t)max_lines_cfg < cells) ? max_lines_cfg : (int)cells;
+    hb->line_stride = (size_t)2 * hb->max_lines;
+    if (want_lines && !hb->lines) CK(cudaMalloc((void**)&hb->lines, (size_t)nframes * 2 * hb->line_stride * sizeof(float)));
+    CK(cudaMemcpyAsync(hb->tabSin, ts.data(), hc.numangle * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(hb->tabCos, tc.data(), hc.numangle * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hb->smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_hough_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb->smem));
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_abi_version(void) { return LFD_ABI_VERSION; }
+
+extern "C" const char* lfd_last_error(const lfd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lfd_destroy(lfd_handle* h)
+{
+    if (!h) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    for (int p = 0; p < 2; p++) {
+        if (h->hb[p].accum) cudaFree(h->hb[p].accum);
+        if (h->hb[p].keys) cudaFree(h->hb[p].keys);
+        if (h->hb[p].lines) cudaFree(h->hb[p].lines);
+        if (h->hb[p].tabSin) cudaFree(h->hb[p].tabSin);
+    }
+    if (h->frames_h) cudaFreeHost(h->frames_h);
+    if (h->res_h) cudaFreeHost(h->res_h);
+    if (h->rects_h) cudaFreeHost(h->rects_h);
+    if (h->rect_off_h) cudaFreeHost(h->rect_off_h);
+    if (h->ctl_h) cudaFreeHost(h->ctl_h);
+    for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return LFD_OK;
+}
+
+static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, const lfd_config* cfg)
+{
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return LFD_E_CUDA; }
+    CK(cudaSetDevice(device));
+    h->device = device;
+    if (max_batch < 1 || H < 8 || W < 8) { h->err = "bad batch or frame size"; return LFD_E_ARG; }
+    if (W % 4 != 0) { h->err = "frame width must be a multiple of 4"; return LFD_E_UNSUPPORTED; }
+    if (W > 4096 || H > 65535) { h->err = "frame too large (W <= 4096, H <= 65535)"; return LFD_E_UNSUPPORTED; }
+    h->B = max_batch;
+    h->d.H = H; h->d.W = W; h->d.WW = (W + 31) / 32; h->d.N = H * W; h->d.NW = H * h->d.WW;
+    memset(&h->cfg, 0, sizeof(h->cfg));
+    if (cfg) h->cfg = *cfg;
+    if (h->cfg.max_runs <= 0) h->cfg.max_runs = 1 << 19;
+    if (h->cfg.max_components <= 0) h->cfg.max_components = 1 << 16;
+    if (h->cfg.max_star_rects <= 0) h->cfg.max_star_rects = 8192;
+    // a frame cannot hold more runs than H * ceil(W/2)
+    long long worst = (long long)H * ((W + 1) / 2);
+    if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
+
+    const int B = h->B;
+    const size_t N = h->d.N, NW = h->d.NW;
+    int rc;
+#define DA(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != LFD_OK) return rc
+    DA(h->in, (size_t)B * N);
+    DA(h->starmask, (size_t)B * NW);
+    DA(h->rects_d, (size_t)B * h->cfg.max_star_rects);
+    DA(h->rect_off_d, (size_t)B + 1);
+    DA(h->hist, (size_t)2 * B * 256);
+    DA(h->lut, (size_t)2 * B * 256);
+    for (int p = 0; p < 2; p++) {
+        DA(h->gray[p], (size_t)B * N);
+        DA(h->morph[p], (size_t)B * N);
+        DA(h->nz[p], (size_t)B * NW);
+        DA(h->cand[p], (size_t)B * NW);
+        DA(h->strong[p], (size_t)B * NW);
+        DA(h->edges[p], (size_t)B * NW);
+        DA(h->box[p], (size_t)B * NW);
+    }
+    DA(h->tap_u8, N);
+    DA(h->ctl, (size_t)B);
+    DA(h->res_d, (size_t)B);
+    DA(h->counters_d, 16);
+    DA(h->segs, (size_t)B * 2 * NW);
+    const int MR = h->cfg.max_runs, MC = h->cfg.max_components;
+    const int slotcap = 2 * MR + 4 * MC, hullcap = 2 * slotcap + 4 * MC;
+    // one slab per field, sliced per frame
+    for (int k = 0; k < 2; k++) {
+        h->ccl_h[k].resize(B);
+        Run* runs; int *parent, *flag, *ymax, *compidx, *rowbase, *rowcnt; u16* wpre;
+        DA(runs, (size_t)B * MR); DA(parent, (size_t)B * MR); DA(flag, (size_t)B * MR); DA(ymax, (size_t)B * MR);
+        DA(compidx, (size_t)B * MR); DA(rowbase, (size_t)B * (H + 1)); DA(wpre, (size_t)B * NW); DA(rowcnt, (size_t)B * H);
+        for (int f = 0; f < B; f++) {
+            CclBuf& c = h->ccl_h[k][f];
+            c.runs = runs + (size_t)f * MR; c.parent = parent + (size_t)f * MR; c.flag = flag + (size_t)f * MR;
+            c.ymax = ymax + (size_t)f * MR; c.compidx = compidx + (size_t)f * MR;
+            c.rowbase = rowbase + (size_t)f * (H + 1); c.wpre = wpre + (size_t)f * NW; c.rowcnt = rowcnt + (size_t)f * H;
+        }
+        DA(h->ccl_d[k], (size_t)B);
+        CK(cudaMemcpy(h->ccl_d[k], h->ccl_h[k].data(), B * sizeof(CclBuf), cudaMemcpyHostToDevice));
+    }
+    h->comp_h.resize(B);
+    {
+        int *root, *y0, *hh, *slot, *hulloff, *rowmin, *rowmax;
+        DA(root, (size_t)B * 2 * MC); DA(y0, (size_t)B * 2 * MC); DA(hh, (size_t)B * 2 * MC);
+        DA(slot, (size_t)B * 2 * MC); DA(hulloff, (size_t)B * 2 * MC);
+        DA(rowmin, (size_t)B * slotcap); DA(rowmax, (size_t)B * slotcap);
+        for (int f = 0; f < B; f++) {
+            CompBuf& c = h->comp_h[f];
+            c.root = root + (size_t)f * 2 * MC; c.y0 = y0 + (size_t)f * 2 * MC; c.h = hh + (size_t)f * 2 * MC;
+            c.slot = slot + (size_t)f * 2 * MC; c.hulloff = hulloff + (size_t)f * 2 * MC;
+            c.rowmin = rowmin + (size_t)f * slotcap; c.rowmax = rowmax + (size_t)f * slotcap;
+            c.slotcap = slotcap; c.hullcap = hullcap; c.maxcomp = MC;
+        }
+    }
+    DA(h->comp_d, (size_t)B);
+    CK(cudaMemcpy(h->comp_d, h->comp_h.data(), B * sizeof(CompBuf), cudaMemcpyHostToDevice));
+    // hull scratch is shared by both passes; rect lists are per pass
+    lfdgeom::Pt* hulls; float* hullfs;
+    DA(hulls, (size_t)B * hullcap); DA(hullfs, (size_t)B * 3 * hullcap);
+    for (int p = 0; p < 2; p++) {
+        h->rbuf_h[p].resize(B);
+        lfd_rect* rects; int* passing;
+        DA(rects, (size_t)B * 2 * MC); DA(passing, (size_t)B * 2 * MC);
+        for (int f = 0; f < B; f++) {
+            RectBuf& r = h->rbuf_h[p][f];
+            r.rects = rects + (size_t)f * 2 * MC; r.passing = passing + (size_t)f * 2 * MC;
+            r.hull = hulls + (size_t)f * hullcap; r.hullf = hullfs + (size_t)f * 3 * hullcap;
+        }
+        DA(h->rbuf_d[p], (size_t)B);
+        CK(cudaMemcpy(h->rbuf_d[p], h->rbuf_h[p].data(), B * sizeof(RectBuf), cudaMemcpyHostToDevice));
+    }
+#undef DA
+    CK(cudaMallocHost((void**)&h->frames_h, (size_t)B * N * sizeof(float)));
+    CK(cudaMallocHost((void**)&h->res_h, (size_t)B * sizeof(lfd_result)));
+    CK(cudaMallocHost((void**)&h->rects_h, (size_t)B * h->cfg.max_star_rects * sizeof(int4)));
+    CK(cudaMallocHost((void**)&h->rect_off_h, ((size_t)B + 1) * sizeof(int)));
+    CK(cudaMallocHost((void**)&h->ctl_h, (size_t)B * sizeof(FrameCtl)));
+    CK(cudaMemset(h->counters_d, 0, 16 * sizeof(int64_t)));
+    memset(h->counters_h, 0, sizeof(h->counters_h));
+    memset(h->timings, 0, sizeof(h->timings));
+    return LFD_OK;
+}
+
+extern "C" int lfd_create_ex(int device, int max_batch, int height, int width, const lfd_config* cfg, lfd_handle** out)
+{
+    if (!out) return LFD_E_ARG;
+    *out = nullptr;
+    lfd_handle* h = new lfd_handle();
+    memset(h->ev_valid, 0, sizeof(h->ev_valid));
+    int rc = create_impl(h, device, max_batch, height, width, cfg);
+    if (rc != LFD_OK) {
+        g_create_error = h->err;
+        lfd_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return LFD_OK;
+}
+
+extern "C" int lfd_create(int device, int max_batch, int height, int width, lfd_handle** out)
+{
+    return lfd_create_ex(device, max_batch, height, width, nullptr, out);
+}
+
+extern "C" int lfd_host_frames(lfd_handle* h, float** out)
+{
+    if (!h || !out) return LFD_E_ARG;
+    *out = h->frames_h;
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------
+static int check_pass_params(lfd_handle* h, const lfd_pass_params& p, bool dim)
+{
+    if (p.nlinesInSet < 1 || p.nlinesInSet > LFD_MAX_SET_LINES) { h->err = "nlinesInSet must be in 1..16"; return LFD_E_UNSUPPORTED; }
+    if (p.contoursMode == 0) { h->err = "contoursMode RETR_EXTERNAL is not implemented"; return LFD_E_UNSUPPORTED; }
+    if (p.contoursMode < 0 || p.contoursMode > 3) { h->err = "unknown contoursMode"; return LFD_E_ARG; }
+    if (p.contoursMethod != 1 && p.contoursMethod != 2) { h->err = "contoursMethod CHAIN_APPROX_TC89_* is not implemented"; return LFD_E_UNSUPPORTED; }
+    if (p.dilate_h < 1 || p.dilate_w < 1) { h->err = "dilateKernel missing"; return LFD_E_ARG; }
+    int eh = dim ? p.erode_h : 0, ew = dim ? p.erode_w : 0;
+    if ((eh > 0) != (ew > 0)) { h->err = "bad erodeKernel"; return LFD_E_ARG; }
+    // combined halo must fit the shared-memory tile padding of k_morph
+    int e_t = eh / 2, e_b = eh > 0 ? eh - 1 - eh / 2 : 0, e_l = ew / 2, e_r = ew > 0 ? ew - 1 - ew / 2 : 0;
+    int d_t = p.dilate_h / 2, d_b = p.dilate_h - 1 - p.dilate_h / 2, d_l = p.dilate_w / 2, d_r = p.dilate_w - 1 - p.dilate_w / 2;
+    if (e_t + d_t > MORPH_PADH || e_b + d_b > MORPH_PADH || e_l + d_l > 12 || e_r + d_r > 11) {
+        h->err = "erode+dilate kernel reach exceeds this build's tile halo (rows <= 16, cols <= 12 left / 11 right)";
+        return LFD_E_UNSUPPORTED;
+    }
+    return LFD_OK;
+}
+
+extern "C" int lfd_set_params(lfd_handle* h, const lfd_params* p)
+{
+    if (!h || !p) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    int rc;
+    if ((rc = check_pass_params(h, p->bright, false)) != LFD_OK) return rc;
+    if ((rc = check_pass_params(h, p->dim, true)) != LFD_OK) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    for (int pass = 0; pass < 2; pass++) {
+        const lfd_pass_params& pp = pass ? p->dim : p->bright;
+        // theta = np.pi/180 and threshold = 1 are literals in the reference (processfield.py:370, :488)
+        rc = hough_setup(h, &h->hb[pass], h->d.H, h->d.W, pp.houghMethod, M_PI / 180, 1, h->B, false, h->cfg.max_lines);
+        if (rc != LFD_OK) return rc;
+    }
+    h->params = *p;
+    h->have_params = true;
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the pipeline
+// ------------------------------------------------------------------------------------------------
+static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
+{
+    const Dims d = h->d;
+    const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
+    cudaStream_t s = h->stream;
+    const bool taps = flags & LFD_KEEP_TAPS;
+    const int tbase = 1 + pass * (T_PER_PASS - 1);   // timing slot of this pass's first stage
+    HoughBufs& hb = h->hb[pass];
+    dim3 rows((d.H + CCL_WARPS - 1) / CCL_WARPS, n);
+
+    k_pass_begin<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, n); LAUNCH_CHECK();
+    // LUT + morphology
+    k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist, h->lut, h->ctl, h->B, d.N, pass); LAUNCH_CHECK();
+    MorphCfg mc;
+    mc.eh = pass ? pp.erode_h : 0; mc.ew = pass ? pp.erode_w : 0; mc.dh = pp.dilate_h; mc.dw = pp.dilate_w;
+    u8* etap = nullptr;
+    if (taps && pass == 1 && mc.eh > 0) {
+        if (!h->eroded_tap) { int rc = dev_alloc(h, &h->eroded_tap, (size_t)h->B * d.N); if (rc) return rc; }
+        etap = h->eroded_tap;
+    }
+    dim3 mg((d.W + MORPH_TW - 1) / MORPH_TW, (d.H + MORPH_TH - 1) / MORPH_TH, n);
+    k_morph<<<mg, 256, 0, s>>>(h->gray[pass], h->lut + (size_t)pass * h->B * 256, h->morph[pass], h->nz[pass], etap,
+                              h->ctl, pass, d, mc); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 1], s));
+    // Sobel + NMS
+    u8* ntap = nullptr;
+    if (taps) {
+        if (!h->nms_tap[pass]) { int rc = dev_alloc(h, &h->nms_tap[pass], (size_t)h->B * d.N); if (rc) return rc; }
+        ntap = h->nms_tap[pass];
+    }
+    dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
+    k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 2], s));
+    // foreground runs: hysteresis + outer contours
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[0], h->ctl, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->edges[pass], h->ctl, pass, d); LAUNCH_CHECK();
+    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->comp_d, h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[0], h->comp_d, h->ctl, pass, d, 0); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 3], s));
+    // background runs: hole contours
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[1], h->ctl, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_merge<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 4], s));
+    // rectangles + box image
+    k_rects<<<dim3(32, n), 128, 0, s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, d, pp.minAreaRectMinLen, pp.lwTresh); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
+    k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], h->ctl, pass, d); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 5], s));
+    // Hough on the morphology output and on the box image
+    CK(cudaMemsetAsync(hb.accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
+    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs, h->ctl, pass, d, (size_t)d.NW); LAUNCH_CHECK();
+    k_hough_vote<<<dim3(8, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs, hb.accum, hb.tabSin, hb.tabCos, h->ctl, pass,
+                                                                            hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
+    int cells = hb.hc.numangle * hb.hc.numrho;
+    int pblocks = (cells + 255) / 256; if (pblocks > 64) pblocks = 64;
+    k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(hb.accum, hb.keys, h->ctl, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
+    k_hough_topk<<<dim3(2, n), 256, 0, s>>>(hb.keys, h->res_d, h->ctl, pass, hb.hc, hb.key_stride, pp.nlinesInSet); LAUNCH_CHECK();
+    if (flags & LFD_FULL_LINES) {
+        if (!hb.lines) CK(cudaMalloc((void**)&hb.lines, (size_t)h->B * 2 * hb.line_stride * sizeof(float)));
+        k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, h->ctl, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
+    }
+    CK(cudaEventRecord(h->ev[tbase + 6], s));
+    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, h->ctl, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh); LAUNCH_CHECK();
+    k_pass_end<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, n, pass, hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[tbase + 7], s));
+    return LFD_OK;
+}
+
+// mode 0: whole-frame pipeline on h->in (un-flipped) ; mode 1/2: standalone bright/dim on frame slot 0
+static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_clipped)
+{
+    const Dims d = h->d;
+    cudaStream_t s = h->stream;
+    if (!h->have_params) { h->err = "lfd_set_params has not been called"; return LFD_E_STATE; }
+    CK(cudaMemsetAsync(h->counters_d, 0, 16 * sizeof(int64_t), s));
+    CK(cudaEventRecord(h->ev[0], s));
+    k_ctl_init<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->res_d, n, mode != 2, mode != 1); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(h->hist, 0, (size_t)2 * h->B * 256 * sizeof(u32), s));
+    if (mode == 0) {
+        CK(cudaMemsetAsync(h->starmask, 0, (size_t)n * d.NW * sizeof(u32), s));
+        int maxr = 0;
+        for (int f = 0; f < n; f++) maxr = max(maxr, h->rect_off_h[f + 1] - h->rect_off_h[f]);
+        if (maxr > 0) { k_star_mask<<<dim3(maxr, n), 128, 0, s>>>(h->rects_d, h->rect_off_d, h->starmask, d); LAUNCH_CHECK(); }
+    }
+    float* clipped = nullptr;
+    if (want_clipped) {
+        if (!h->clipped) { int rc = dev_alloc(h, &h->clipped, (size_t)d.N); if (rc) return rc; }
+        clipped = h->clipped;
+    }
+    const lfd_pass_params& pd = h->params.dim;
+    int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 592) pblocks = 592;   // 4 CTAs per SM on 148 SMs
+    k_prep<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, h->hist + (size_t)h->B * 256,
+                                          clipped, d, mode, (flags & LFD_INPUT_BIGENDIAN) ? 1 : 0, (float)pd.minFlux,
+                                          (float)pd.addFlux); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[1], s));
+    int rc;
+    if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags)) != LFD_OK) return rc; }
+    else for (int i = 2; i <= T_PER_PASS; i++) CK(cudaEventRecord(h->ev[i], s));
+    if (mode != 1) { if ((rc = run_pass_kernels(h, n, 1, flags)) != LFD_OK) return rc; }
+    else for (int i = T_PER_PASS + 1; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+    CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[N_TIMINGS], s));
+    h->last_n = n; h->last_flags = flags; h->pending = true;
+    return LFD_OK;
+}
+
+static int stage_rects(lfd_handle* h, int n, const int32_t* rects, const int32_t* rect_offsets)
+{
+    if (!rects || !rect_offsets) {
+        for (int f = 0; f <= n; f++) h->rect_off_h[f] = 0;
+    } else {
+        if (rect_offsets[0] != 0) { h->err = "rect_offsets[0] must be 0"; return LFD_E_ARG; }
+        for (int f = 0; f < n; f++) {
+            int c = rect_offsets[f + 1] - rect_offsets[f];
+            if (c < 0 || c > h->cfg.max_star_rects) { h->err = "too many star rectangles for a frame (lfd_config.max_star_rects)"; return LFD_E_CAPACITY; }
+        }
+        memcpy(h->rect_off_h, rect_offsets, ((size_t)n + 1) * sizeof(int));
+        memcpy(h->rects_h, rects, (size_t)rect_offsets[n] * sizeof(int4));
+        CK(cudaMemcpyAsync(h->rects_d, h->rects_h, (size_t)rect_offsets[n] * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->rect_off_d, h->rect_off_h, ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return LFD_OK;
+}
+
+extern "C" int lfd_upload(lfd_handle* h, const float* frames, int n, const int32_t* rects, const int32_t* rect_offsets, int flags)
+{
+    if (!h || n < 1 || n > h->B) { if (h) h->err = "bad batch size"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    int rc = stage_rects(h, n, rects, rect_offsets);
+    if (rc != LFD_OK) return rc;
+    const float* src = frames ? frames : h->frames_h;
+    CK(cudaMemcpyAsync(h->in, src, (size_t)n * h->d.N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->last_flags = flags;
+    return LFD_OK;
+}
+
+extern "C" int lfd_submit(lfd_handle* h, const float* frames, int n, const int32_t* rects, const int32_t* rect_offsets, int flags)
+{
+    int rc = lfd_upload(h, frames, n, rects, rect_offsets, flags);
+    if (rc != LFD_OK) return rc;
+    return run_pipeline(h, n, flags, 0, false);
+}
+
+extern "C" int lfd_run_resident(lfd_handle* h, int n, int flags)
+{
+    if (!h || n < 1 || n > h->B) { if (h) h->err = "bad batch size"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    return run_pipeline(h, n, flags, 0, false);
+}
+
+extern "C" int lfd_wait(lfd_handle* h, lfd_result* out)
+{
+    if (!h) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    if (!h->pending) { h->err = "nothing submitted"; return LFD_E_STATE; }
+    h->pending = false;
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < N_TIMINGS; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+        h->timings[i] = ms;
+    }
+    if (out) memcpy(out, h->res_h, (size_t)h->last_n * sizeof(lfd_result));
+    return LFD_OK;
+}
+
+extern "C" int lfd_run_pass(lfd_handle* h, int pass, float* img, int flags, int writeback, lfd_result* out)
+{
+    if (!h || !img || (pass != 0 && pass != 1)) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    h->rect_off_h[0] = h->rect_off_h[1] = 0;
+    CK(cudaMemcpyAsync(h->in, img, (size_t)h->d.N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = run_pipeline(h, 1, flags, pass == 0 ? 1 : 2, writeback != 0);
+    if (rc != LFD_OK) return rc;
+    if (writeback) CK(cudaMemcpyAsync(img, h->clipped, (size_t)h->d.N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    return lfd_wait(h, out);
+}
+
+// remove_stars' blot on a host image
+__global__ void k_blot(float* img, const int4* rects, int nrects, Dims d)
+{
+    int ri = blockIdx.x;
+    if (ri >= nrects) return;
+    int4 r = rects[ri];
+    int r0 = max(r.x, 0), r1 = min(r.y, d.H), c0 = max(r.z, 0), c1 = min(r.w, d.W);
+    if (r0 >= r1 || c0 >= c1) return;
+    int w = c1 - c0, total = (r1 - r0) * w;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) img[(size_t)(r0 + i / w) * d.W + c0 + i % w] = 0.0f;
+}
+
+extern "C" int lfd_blot(lfd_handle* h, float* img, const int32_t* rects, int nrects)
+{
+    if (!h || !img || nrects < 0 || (nrects > 0 && !rects)) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    if (nrects > h->B * h->cfg.max_star_rects) { h->err = "too many rectangles"; return LFD_E_CAPACITY; }
+    if (nrects == 0) return LFD_OK;
+    memcpy(h->rects_h, rects, (size_t)nrects * sizeof(int4));
+    CK(cudaMemcpyAsync(h->rects_d, h->rects_h, (size_t)nrects * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->in, img, (size_t)h->d.N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    k_blot<<<nrects, 128, 0, h->stream>>>(h->in, h->rects_d, nrects, h->d); LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(img, h->in, (size_t)h->d.N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// taps
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_get_stage_count(lfd_handle* h, int frame, int pass, int stage, int* count)
+{
+    if (!h || !count || frame < 0 || frame >= h->last_n || (pass != 0 && pass != 1)) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    const HoughBufs& hb = h->hb[pass];
+    switch (stage) {
+    case LFD_STAGE_RECTS: {
+        *count = min(h->ctl_h[frame].ncomp_saved[pass][0], h->cfg.max_components) + min(h->ctl_h[frame].ncomp_saved[pass][1], h->cfg.max_components);
+        return LFD_OK;
+    }
+    case LFD_STAGE_LINES_EQU: *count = h->res_h[frame].n_lines_equ[pass]; return LFD_OK;
+    case LFD_STAGE_LINES_BOX: *count = h->res_h[frame].n_lines_box[pass]; return LFD_OK;
+    case LFD_STAGE_ACCUM_EQU:
+    case LFD_STAGE_ACCUM_BOX: *count = (int)hb.accum_stride; return LFD_OK;
+    default: h->err = "stage has no count"; return LFD_E_ARG;
+    }
+}
+
+extern "C" int lfd_get_stage(lfd_handle* h, int frame, int pass, int stage, void* host_out, size_t bytes)
+{
+    if (!h || !host_out || frame < 0 || frame >= h->last_n || (pass != 0 && pass != 1)) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "batch still pending (call lfd_wait)"; return LFD_E_STATE; }
+    const Dims d = h->d;
+    cudaStream_t s = h->stream;
+    const size_t N = d.N;
+    Dims d1 = d;
+    const void* src = nullptr;
+    size_t need = N;
+    HoughBufs& hb = h->hb[pass];
+    switch (stage) {
+    case LFD_STAGE_MASK:
+        k_expand_mask<<<dim3(256, 1), 256, 0, s>>>(h->starmask + (size_t)frame * d.NW, h->tap_u8, d1); LAUNCH_CHECK();
+        src = h->tap_u8; break;
+    case LFD_STAGE_GRAY: src = h->gray[pass] + (size_t)frame * N; break;
+    case LFD_STAGE_EQU:
+        k_apply_lut<<<dim3(256, 1), 256, 0, s>>>(h->gray[pass] + (size_t)frame * N, h->lut + ((size_t)pass * h->B + frame) * 256, h->tap_u8, d1); LAUNCH_CHECK();
+        src = h->tap_u8; break;
+    case LFD_STAGE_ERODED:
+        if (!h->eroded_tap || pass != 1) { h->err = "eroded tap not recorded (dim pass with LFD_KEEP_TAPS)"; return LFD_E_STATE; }
+        src = h->eroded_tap + (size_t)frame * N; break;
+    case LFD_STAGE_MORPH: src = h->morph[pass] + (size_t)frame * N; break;
+    case LFD_STAGE_CANNY:
+        k_expand_mask<<<dim3(256, 1), 256, 0, s>>>(h->edges[pass] + (size_t)frame * d.NW, h->tap_u8, d1); LAUNCH_CHECK();
+        src = h->tap_u8; break;
+    case LFD_STAGE_BOX:
+        k_expand_mask<<<dim3(256, 1), 256, 0, s>>>(h->box[pass] + (size_t)frame * d.NW, h->tap_u8, d1); LAUNCH_CHECK();
+        src = h->tap_u8; break;
+    case LFD_STAGE_HIST: src = h->hist + ((size_t)pass * h->B + frame) * 256; need = 256 * sizeof(u32); break;
+    case LFD_STAGE_LUT: src = h->lut + ((size_t)pass * h->B + frame) * 256; need = 256; break;
+    case LFD_STAGE_NMS:
+        if (!h->nms_tap[pass]) { h->err = "NMS tap not recorded (LFD_KEEP_TAPS)"; return LFD_E_STATE; }
+        src = h->nms_tap[pass] + (size_t)frame * N; break;
+    case LFD_STAGE_FG_LABELS:
+    case LFD_STAGE_BG_LABELS: {
+        if (!h->labels_tap) { int rc = dev_alloc(h, &h->labels_tap, N); if (rc) return rc; }
+        int kind = stage == LFD_STAGE_BG_LABELS;
+        k_ccl_labels<<<(d.H + CCL_WARPS - 1) / CCL_WARPS, CCL_WARPS * 32, 0, s>>>(h->ccl_d[kind], h->labels_tap, h->ctl, pass, d, kind, frame); LAUNCH_CHECK();
+        src = h->labels_tap; need = N * sizeof(int); break;
+    }
+    case LFD_STAGE_RECTS: {
+        int n0 = min(h->ctl_h[frame].ncomp_saved[pass][0], h->cfg.max_components), n1 = min(h->ctl_h[frame].ncomp_saved[pass][1], h->cfg.max_components);
+        need = (size_t)(n0 + n1) * sizeof(lfd_rect);
+        if (bytes < need) { h->err = "buffer too small"; return LFD_E_ARG; }
+        const RectBuf& rb = h->rbuf_h[pass][frame];
+        if (n0) CK(cudaMemcpyAsync(host_out, rb.rects, (size_t)n0 * sizeof(lfd_rect), cudaMemcpyDeviceToHost, s));
+        if (n1) CK(cudaMemcpyAsync((char*)host_out + (size_t)n0 * sizeof(lfd_rect), rb.rects + h->cfg.max_components, (size_t)n1 * sizeof(lfd_rect), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return LFD_OK;
+    }
+    case LFD_STAGE_ACCUM_EQU:
+    case LFD_STAGE_ACCUM_BOX:
+        src = hb.accum + ((size_t)frame * 2 + (stage == LFD_STAGE_ACCUM_BOX)) * hb.accum_stride;
+        need = hb.accum_stride * sizeof(int); break;
+    case LFD_STAGE_LINES_EQU:
+    case LFD_STAGE_LINES_BOX: {
+        if (!hb.lines || !(h->last_flags & LFD_FULL_LINES)) { h->err = "full line lists not recorded (LFD_FULL_LINES)"; return LFD_E_STATE; }
+        int which = stage == LFD_STAGE_LINES_BOX;
+        int nl = which ? h->res_h[frame].n_lines_box[pass] : h->res_h[frame].n_lines_equ[pass];
+        if (nl < 0) nl = 0;
+        if (nl > hb.max_lines) nl = hb.max_lines;
+        src = hb.lines + ((size_t)frame * 2 + which) * hb.line_stride;
+        need = (size_t)nl * 2 * sizeof(float);
+        if (need == 0) return LFD_OK;
+        break;
+    }
+    case LFD_STAGE_CLIPPED:
+        if (!h->clipped) { h->err = "clipped image not recorded"; return LFD_E_STATE; }
+        src = h->clipped; need = N * sizeof(float); break;
+    default: h->err = "unknown stage"; return LFD_E_ARG;
+    }
+    if (bytes < need) { h->err = "buffer too small"; return LFD_E_ARG; }
+    CK(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone cv2.HoughLines
+// ------------------------------------------------------------------------------------------------
+struct HoughScratch {
+    int H = 0, W = 0;
+    u8* img = nullptr; u32* mask = nullptr; uint2* segs = nullptr; FrameCtl* ctl = nullptr; lfd_result* res = nullptr;
+    HoughBufs hb;
+};
+static HoughScratch g_hs;   // one per process is enough for the microbenchmark entry point
+
+extern "C" int lfd_hough_dims(int height, int width, double rho, double theta, int* numangle, int* numrho)
+{
+    if (!numangle || !numrho || !(rho > 0) || !(theta > 0)) return LFD_E_ARG;
+    hough_dims_host(height, width, rho, theta, numangle, numrho);
+    return LFD_OK;
+}
+
+extern "C" int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, double rho, double theta,
+                               int threshold, float* lines, int max_lines, int* n_lines, int32_t* accum)
+{
+    if (!h || !img || height < 1 || width < 1 || height > 65535 || width > 65535 * 32) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    cudaStream_t s = h->stream;
+    Dims d; d.H = height; d.W = width; d.WW = (width + 31) / 32; d.N = height * width; d.NW = height * d.WW;
+    HoughScratch& hs = g_hs;
+    if (hs.H != height || hs.W != width) {
+        if (hs.img) { cudaFree(hs.img); cudaFree(hs.mask); cudaFree(hs.segs); cudaFree(hs.ctl); cudaFree(hs.res); }
+        hs.img = nullptr;
+        CK(cudaMalloc((void**)&hs.img, (size_t)d.N));
+        CK(cudaMalloc((void**)&hs.mask, (size_t)d.NW * sizeof(u32)));
+        CK(cudaMalloc((void**)&hs.segs, (size_t)2 * d.NW * sizeof(uint2)));
+        CK(cudaMalloc((void**)&hs.ctl, sizeof(FrameCtl)));
+        CK(cudaMalloc((void**)&hs.res, sizeof(lfd_result)));
+        hs.H = height; hs.W = width;
+    }
+    int rc = hough_setup(h, &hs.hb, height, width, rho, theta, threshold, 1, true, 0);
+    if (rc != LFD_OK) return rc;
+    HoughBufs& hb = hs.hb;
+    CK(cudaMemcpyAsync(hs.img, img, (size_t)d.N, cudaMemcpyHostToDevice, s));
+    k_ctl_init<<<1, 32, 0, s>>>(hs.ctl, hs.res, 1, 1, 0); LAUNCH_CHECK();
+    // mark Hough as enabled for pass 0
+    FrameCtl c; memset(&c, 0, sizeof(c)); c.active[0] = 1; c.hough[0] = 1;
+    CK(cudaMemcpyAsync(hs.ctl, &c, sizeof(c), cudaMemcpyHostToDevice, s));
+    k_pack_mask<<<592, 256, 0, s>>>(hs.img, hs.mask, d); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(hb.accum, 0, (size_t)2 * hb.accum_stride * sizeof(int), s));
+    // which = 0 only: pass the same mask twice and ignore slot 1
+    k_hough_compact<<<dim3(64, 1, 1), 256, 0, s>>>(hs.mask, hs.mask, hs.segs, hs.ctl, 0, d, (size_t)d.NW); LAUNCH_CHECK();
+    k_hough_vote<<<dim3(32, hb.hc.ngroups, 1), HOUGH_THREADS, hb.smem, s>>>(hs.segs, hb.accum, hb.tabSin, hb.tabCos, hs.ctl, 0, hb.hc,
+                                                                         (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
+    long long cells = (long long)hb.hc.numangle * hb.hc.numrho;
+    int pblocks = (int)((cells + 255) / 256); if (pblocks > 1184) pblocks = 1184;
+    k_hough_peaks<<<dim3(pblocks, 1), 256, 0, s>>>(hb.accum, hb.keys, hs.ctl, 0, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
+    k_hough_sort<<<dim3(1, 1), 1024, 0, s>>>(hb.keys, hb.lines, hs.ctl, 0, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
+    FrameCtl out;
+    CK(cudaMemcpyAsync(&out, hs.ctl, sizeof(out), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int np = out.npeaks[0];
+    if (n_lines) *n_lines = np;
+    int ncopy = np < max_lines ? np : max_lines;
+    if (ncopy > hb.max_lines) ncopy = hb.max_lines;
+    if (lines && ncopy > 0) CK(cudaMemcpy(lines, hb.lines, (size_t)ncopy * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (accum) CK(cudaMemcpy(accum, hb.accum, hb.accum_stride * sizeof(int), cudaMemcpyDeviceToHost));
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries)
+{
+    if (!h || !ms) return LFD_E_ARG;
+    int n = N_TIMINGS < max_entries ? N_TIMINGS : max_entries;
+    for (int i = 0; i < n; i++) ms[i] = h->timings[i];
+    if (n_entries) *n_entries = n;
+    return LFD_OK;
+}
+
+extern "C" const char* lfd_timing_name(int i) { return (i >= 0 && i < N_TIMINGS) ? k_timing_names[i] : ""; }
+
+extern "C" int64_t lfd_kernel_launches(const lfd_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int lfd_get_counters(lfd_handle* h, int64_t* out, int n)
+{
+    if (!h || !out) return LFD_E_ARG;
+    for (int i = 0; i < n && i < 16; i++) out[i] = h->counters_h[i];
+    return LFD_OK;
+}

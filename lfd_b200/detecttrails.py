@@ -1,0 +1,307 @@
+"""Drop-in for ``lfd.detecttrails.detecttrails``: ``DetectTrails`` and ``process_field``.
+
+Mirrors /root/reference/lfd/detecttrails/detecttrails.py: constructor kwargs and defaults (:199-267,
+including the quirk that ``params_dim=`` / ``params_removestars=`` kwargs land in ``params_bright``,
+:253-256), frame-set selection ``_load`` (:290-342), loop order and ranges of ``process`` (:344-407,
+``run-camcol`` strides fields by 50, ``endfield`` excluded), the results line (:115-117,127,131 - seven
+of its brace groups are literal text in the reference and stay literal here), per-frame error capture
+into errors.txt (:133-139) and the bz2 unpack path (:81-111).
+
+What differs is where the work runs: frames are decoded on the host, grouped into batches, copied with
+pinned cudaMemcpyAsync and pushed through liblfd_b200.so (one handle per GPU); results come back as one
+small struct per frame and are written in the reference's frame order.
+"""
+import bz2
+import os
+import traceback
+
+import numpy as _np
+
+from . import _lib, sdssfiles as files
+from .processfield import result_from_device, setup_debug
+from .removestars import read_photoObj_arrays, star_rects
+
+try:
+    import fitsio
+except ImportError:  # pragma: no cover - depends on the image
+    from . import fitsio_lite as fitsio
+
+# cv2 enum values the reference re-exports (detecttrails.py:14-18); cv2 itself is not needed here
+RETR_EXTERNAL, RETR_LIST, RETR_CCOMP, RETR_TREE = 0, 1, 2, 3
+CHAIN_APPROX_NONE, CHAIN_APPROX_SIMPLE, CHAIN_APPROX_TC89_L1, CHAIN_APPROX_TC89_KCOS = 1, 2, 3, 4
+
+__all__ = ["DetectTrails", "process_field", "process_fields", "default_params"]
+
+
+def default_params():
+    """The three default dicts of detecttrails.py:202-239."""
+    params_bright = {
+        "lwTresh": 5, "thetaTresh": 0.15, "dilateKernel": _np.ones((4, 4), _np.uint8),
+        "contoursMode": RETR_LIST, "contoursMethod": CHAIN_APPROX_NONE, "minAreaRectMinLen": 1,
+        "houghMethod": 20, "nlinesInSet": 3, "lineSetTresh": 0.15, "dro": 25, "debug": False}
+    params_dim = {
+        "minFlux": 0.02, "addFlux": 0.5, "lwTresh": 5, "thetaTresh": 0.15,
+        "erodeKernel": _np.ones((3, 3), _np.uint8), "dilateKernel": _np.ones((9, 9), _np.uint8),
+        "contoursMode": RETR_LIST, "contoursMethod": CHAIN_APPROX_NONE, "minAreaRectMinLen": 1,
+        "houghMethod": 20, "nlinesInSet": 3, "lineSetTresh": 0.15, "dro": 20, "debug": False}
+    params_removestars = {
+        "pixscale": 0.396, "defaultxy": 20, "maxxy": 60,
+        "filter_caps": {"u": 22.0, "g": 22.2, "r": 22.2, "i": 21.3, "z": 20.5},
+        "magcount": 3, "maxmagdiff": 3, "debug": False}
+    return params_bright, params_dim, params_removestars
+
+
+def _load_frame(run, camcol, filter, field):
+    """detecttrails.py:73-117: resolve the path, unpack .bz2 if needed, read image + header.
+    Returns (img, header_prefix_of_the_results_line)."""
+    removefits = False
+    fitspath = None
+    try:
+        origfitspath = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
+        if not os.path.exists(origfitspath):
+            bzpath = origfitspath + ".bz2"
+            if not os.path.exists(bzpath):
+                errmsg = ("File {0} or its bz2 compressed version not found. Are you sure they exist?")
+                raise FileNotFoundError(errmsg.format(origfitspath))
+            with open(bzpath, "rb") as compressedfits:
+                fitsdata = bz2.decompress(compressedfits.read())
+            try:
+                fitsdmp = os.environ["FITS_DUMP"]
+            except KeyError:
+                fitsdmp = os.path.join(os.path.split(__file__)[0], "fits_dump/")
+                os.makedirs(fitsdmp, exist_ok=True)
+            fitspath = os.path.join(fitsdmp, os.path.split(origfitspath)[-1])
+            with open(fitspath, "wb") as decompressed:
+                decompressed.write(fitsdata)
+            removefits = True
+        else:
+            fitspath = origfitspath
+        img = fitsio.read(fitspath)
+        h = fitsio.read_header(fitspath)
+        # only the first fragment is an f-string in the reference (detecttrails.py:115-117)
+        printit = (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
+                   "{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
+                   "{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
+        return img, printit
+    finally:
+        if removefits:
+            os.remove(fitspath)
+
+
+def _write_error(errors, run, camcol, filter, field, exc, debug):
+    """detecttrails.py:133-139."""
+    if debug:
+        traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
+    errors.write(f"{run} {camcol} {filter} {field}\n")
+    traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3, file=errors)
+    errors.write(str(exc) + "\n\n")
+
+
+_handles = {}
+
+
+def _batch_handle(shape, batch, device):
+    key = (shape, device)
+    h = _handles.get(key)
+    if h is None or h.B < batch:
+        if h is not None:
+            h.close()
+        h = _lib.Handle(shape[0], shape[1], max_batch=batch, device=device)
+        _handles[key] = h
+    return h
+
+
+def process_fields(results, errors, frames, params_bright, params_dim, params_removestars, batch=16, device=0):
+    """Process an ordered list of (run, camcol, filter, field) in GPU batches; results/errors are written
+    in list order, exactly the lines the reference's per-frame loop would write."""
+    debug = bool(params_bright["debug"] or params_dim["debug"])
+    frames = list(frames)
+    for i0 in range(0, len(frames), batch):
+        chunk = frames[i0:i0 + batch]
+        loaded = []          # per frame: ("ok", img, rects, printit) or ("err", exc)
+        for (run, camcol, filter, field) in chunk:
+            try:
+                img, printit = _load_frame(run, camcol, filter, field)
+                cat = read_photoObj_arrays(files.filename("photoObj", run=run, camcol=camcol, field=field))
+                rp = {k: v for k, v in params_removestars.items()}
+                rects = star_rects(cat, filter, img.shape, **rp)
+                if img.dtype != _np.float32:
+                    img = img.astype(_np.float32)
+                loaded.append(("ok", img, rects, printit))
+            except Exception as e:   # noqa: BLE001 - the reference swallows everything per frame
+                loaded.append(("err", e))
+        # frames of one shape go to the device together
+        by_shape = {}
+        for j, item in enumerate(loaded):
+            if item[0] == "ok":
+                by_shape.setdefault(item[1].shape, []).append(j)
+        outcome = {}
+        for shape, idxs in by_shape.items():
+            try:
+                h = _batch_handle(shape, max(batch, 1), device)
+                h.set_params(params_bright, params_dim)
+                for k, j in enumerate(idxs):
+                    h.host_frames[k] = loaded[j][1]
+                h.submit(len(idxs), [loaded[j][2] for j in idxs], flags=0)
+                res = h.wait()
+                for k, j in enumerate(idxs):
+                    try:
+                        r = res[k]
+                        if r.status & _lib.FRAME_OVERFLOW:
+                            raise _lib.LfdError(_lib.LFD_E_CAPACITY, "per-frame work list overflow")
+                        det, out = (False, None)
+                        for p in (0, 1):
+                            if r.rect_detection[p] >= 0:
+                                det, out = result_from_device(r, p, shape)
+                                if det:
+                                    break
+                        outcome[j] = ("ok", det, out)
+                    except Exception as e:   # noqa: BLE001
+                        outcome[j] = ("err", e)
+            except Exception as e:   # noqa: BLE001
+                for j in idxs:
+                    outcome[j] = ("err", e)
+        for j, (run, camcol, filter, field) in enumerate(chunk):
+            item = loaded[j]
+            if item[0] == "err":
+                _write_error(errors, run, camcol, filter, field, item[1], debug)
+                continue
+            o = outcome[j]
+            if o[0] == "err":
+                _write_error(errors, run, camcol, filter, field, o[1], debug)
+            elif o[1]:
+                res = o[2]
+                results.write(item[3] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n")
+
+
+def process_field(results, errors, run, camcol, filter, field, params_bright, params_dim, params_removestars):
+    """detecttrails.py:30-143 for one frame."""
+    process_fields(results, errors, [(run, camcol, filter, field)], params_bright, params_dim,
+                   params_removestars, batch=1)
+
+
+class DetectTrails:
+    """Convenience class that processes targeted SDSS frames (detecttrails.py:146-407).
+
+    Extra, optional kwargs that the reference does not have: ``batch`` (frames per GPU batch,
+    default 16) and ``device`` (CUDA device index, default 0)."""
+
+    def __init__(self, **kwargs):
+        savepth = (kwargs["savepath"] if "savepath" in kwargs else ".")
+        self.kwargs = kwargs
+        self.params_bright, self.params_dim, self.params_removestars = default_params()
+        self.batch = int(kwargs.get("batch", 16))
+        self.device = int(kwargs.get("device", 0))
+
+        if "results" in kwargs:
+            self.results = kwargs["results"]
+        else:
+            self.results = os.path.join(savepth, "results.txt")
+        if "errors" in kwargs:
+            self.errors = kwargs["errors"]
+        else:
+            self.errors = os.path.join(savepth, "errors.txt")
+
+        # reference behaviour, kept on purpose: all three land in params_bright (detecttrails.py:251-256)
+        if "params_bright" in kwargs:
+            self.params_bright = kwargs["params_bright"]
+        if "params_dim" in kwargs:
+            self.params_bright = kwargs["params_dim"]
+        if "params_removestars" in kwargs:
+            self.params_bright = kwargs["params_removestars"]
+
+        if "debug" in kwargs:
+            self.debug = kwargs.pop("debug")
+            self.params_bright["debug"] = self.debug
+            self.params_dim["debug"] = self.debug
+            self.params_removestars["debug"] = self.debug
+        if any([self.params_removestars["debug"], self.params_bright["debug"], self.params_dim["debug"]]):
+            setup_debug()
+
+        self._load()
+
+    def _runInfo(self):
+        rl = files.runlist()
+        w, = _np.where(rl["run"] == self._run)
+        if len(w) == 0:
+            raise ValueError("Run %s not found in runList.par" % self._run)
+        return rl[w]["startfield"][0], rl[w]["endfield"][0]
+
+    def _getRuns(self):
+        rl = files.runlist()
+        runs = rl["run"]
+        if runs is None:
+            raise ValueError("Unable to retrieve runs. Retrieved NoneType.")
+        return runs
+
+    def _load(self):
+        """kwargs -> self._pick (detecttrails.py:290-342)."""
+        self._run, self._camcol, self._field = int(0), int(0), int(0)
+        self._filter, self._pick = str(0), str(0)
+        kwargs = self.kwargs
+        if "run" in kwargs:
+            self._run = kwargs["run"]
+            self._pick = "run"
+        if "camcol" in kwargs:
+            if kwargs["camcol"] not in (1, 2, 3, 4, 5, 6):
+                raise ValueError("Nonexisting camcol")
+            self._camcol = kwargs["camcol"]
+            self._pick = "run-camcol"
+        if "field" in kwargs or "frame" in kwargs:
+            if self._camcol == 0:
+                raise ValueError("send camcol= ")
+            self._field = kwargs["field"] if "field" in kwargs else kwargs["frame"]
+        if "filter" in kwargs:
+            if kwargs["filter"] not in ("u", "g", "r", "i", "z"):
+                raise ValueError("Nonexistting filter")
+            self._filter = kwargs["filter"]
+            if self._camcol != 0:
+                self._pick = "camcol-filter"
+            if self._run != 0:
+                self._pick = "run-filter"
+            if (self._camcol != 0) and (self._run != 0):
+                self._pick = "run-camcol-filter"
+        if "filter" not in kwargs:
+            if (self._field != 0) and (self._camcol != 0):
+                self._pick = "camcol-frame"
+        if (self._field != 0) and (self._camcol != 0) and (self._filter != "0"):
+            self._pick = "field"
+
+    def frame_list(self):
+        """The (run, camcol, filter, field) sequence ``process`` visits, in the reference's order."""
+        out = []
+        filters = ("u", "g", "r", "i", "z")
+        camcols = (1, 2, 3, 4, 5, 6)
+        if self._pick == "camcol-filter":
+            for _run in self._getRuns():
+                self._run = _run
+                startfield, endfield = self._runInfo()
+                out += [(_run, self._camcol, self._filter, f) for f in range(startfield, endfield, 1)]
+            self._run = 0
+        if self._pick == "run":
+            startfield, endfield = self._runInfo()
+            for c in camcols:
+                for flt in filters:
+                    out += [(self._run, c, flt, f) for f in range(startfield, endfield, 1)]
+        if self._pick == "run-filter":
+            startfield, endfield = self._runInfo()
+            for c in camcols:
+                out += [(self._run, c, self._filter, f) for f in range(startfield, endfield, 1)]
+        if self._pick == "run-camcol":
+            startfield, endfield = self._runInfo()
+            for flt in filters:
+                out += [(self._run, self._camcol, flt, f) for f in range(startfield, endfield, 50)]
+        if self._pick == "run-camcol-filter":
+            startfield, endfield = self._runInfo()
+            out += [(self._run, self._camcol, self._filter, f) for f in range(startfield, endfield, 1)]
+        if self._pick == "camcol-frame":
+            out += [(self._run, self._camcol, flt, self._field) for flt in filters]
+        if self._pick == "field":
+            out.append((self._run, self._camcol, self._filter, self._field))
+        return out
+
+    def process(self):
+        """Run the selected frames; results/errors files are opened in append mode like the original."""
+        with open(self.results, "a") as results, open(self.errors, "a") as errors:
+            process_fields(results, errors, self.frame_list(), self.params_bright, self.params_dim,
+                           self.params_removestars, batch=self.batch, device=self.device)

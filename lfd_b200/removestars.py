@@ -1,0 +1,99 @@
+"""Drop-in for ``lfd.detecttrails.removestars``: catalog filter on the host (vectorised NumPy with the
+reference's exact ceil/compare rules), square blots on the device.
+
+Mirrors /root/reference/lfd/detecttrails/removestars.py: ``read_photoObj`` (:63-132) and
+``remove_stars`` (:148-233) keep their names, arguments and return values; the deprecated CSV
+functions (:19-60, :135-145) are unreachable from ``process_field`` and are not provided.
+"""
+import math
+
+import numpy as np
+
+from . import _lib, sdssfiles as files
+
+try:  # the reference imports fitsio unconditionally; it is optional here
+    import fitsio
+except ImportError:  # pragma: no cover - depends on the image
+    from . import fitsio_lite as fitsio
+
+__all__ = ["read_photoObj", "remove_stars", "star_rects", "read_photoObj_arrays"]
+
+_BANDS = ("u", "g", "r", "i", "z")
+
+
+def read_photoObj_arrays(path_to_photoOBJ):
+    """The eight columns removestars.py:97-104 reads, as arrays."""
+    data, _hdr = fitsio.read(path_to_photoOBJ, header="True")
+    return {k: np.asarray(data[k]) for k in
+            ("OBJC_TYPE", "TYPE", "ROWC", "COLC", "PETROTH90", "PSFMAG", "NOBSERVE", "NDETECT")}
+
+
+def _ceil_int(a):
+    """math.ceil element-wise -> int64; non-finite input raises like math.ceil does (removestars.py:113-130)."""
+    a = np.asarray(a, np.float64)
+    if not np.all(np.isfinite(a)):
+        if np.any(np.isnan(a)):
+            raise ValueError("cannot convert float NaN to integer")
+        raise OverflowError("cannot convert float infinity to integer")
+    return np.ceil(a).astype(np.int64)
+
+
+def read_photoObj(path_to_photoOBJ):
+    """removestars.py:63-132: lists of per-band dicts of ceil'd values plus the raw type/count columns."""
+    c = read_photoObj_arrays(path_to_photoOBJ)
+    def dicts(a):
+        a = _ceil_int(a)
+        return [dict(zip(_BANDS, (int(v) for v in row))) for row in a]
+    return (dicts(c["ROWC"]), dicts(c["COLC"]), dicts(c["PSFMAG"]), dicts(c["PETROTH90"]),
+            c["OBJC_TYPE"], c["TYPE"], c["NOBSERVE"], c["NDETECT"])
+
+
+def star_rects(cat, _filter, shape, defaultxy, filter_caps, maxxy, pixscale, magcount, maxmagdiff, debug=False):
+    """Blot rectangles (row_start, row_stop, col_start, col_stop) on the un-flipped image.
+
+    Filter logic of removestars.py:212-230, vectorised; the slice ``img[x-dxy:x+dxy, y-dxy:y+dxy]``
+    (:231) is resolved with Python's own slice arithmetic so that objects whose start goes negative
+    wrap to an empty slice exactly like NumPy's indexing does."""
+    b = _BANDS.index(_filter)
+    H, W = shape
+    rows = _ceil_int(cat["ROWC"]); cols = _ceil_int(cat["COLC"])
+    mags = _ceil_int(cat["PSFMAG"]); p90 = _ceil_int(cat["PETROTH90"])
+    n = len(rows)
+    if n == 0:
+        return np.zeros((0, 4), np.int32)
+    keep = mags[:, b] < filter_caps[_filter]
+    big = np.zeros(n, np.int64)
+    for j in range(5):
+        for k in range(j + 1, 5):
+            big += np.abs(mags[:, j] - mags[:, k]) > maxmagdiff
+    keep &= magcount >= big
+    keep &= np.asarray(cat["NOBSERVE"]) == np.asarray(cat["NDETECT"])
+    dxy = np.full(n, defaultxy, np.int64)
+    pos = p90[:, b] > 0
+    dxy[pos] = (p90[pos, b] / pixscale).astype(np.int64) + 10     # int() truncation of a positive float
+    dxy[dxy > maxxy] = defaultxy
+    out = []
+    x, y = cols[:, b], rows[:, b]
+    for i in np.flatnonzero(keep):
+        r0, r1, _ = slice(int(x[i] - dxy[i]), int(x[i] + dxy[i])).indices(H)
+        c0, c1, _ = slice(int(y[i] - dxy[i]), int(y[i] + dxy[i])).indices(W)
+        if r0 < r1 and c0 < c1:
+            out.append((r0, r1, c0, c1))
+    return np.asarray(out, np.int32).reshape(-1, 4)
+
+
+def remove_stars(img, _run, _camcol, _filter, _field, defaultxy, filter_caps, maxxy, pixscale, magcount,
+                 maxmagdiff, debug):
+    """removestars.py:148-233: zero a square per catalog object, in place, and return ``img``."""
+    cat = read_photoObj_arrays(files.filename("photoObj", run=_run, camcol=_camcol, field=_field))
+    rects = star_rects(cat, _filter, img.shape, defaultxy, filter_caps, maxxy, pixscale, magcount, maxmagdiff, debug)
+    if len(rects) == 0:
+        return img
+    work = img
+    if img.dtype != np.float32 or not img.flags["C_CONTIGUOUS"]:
+        work = np.ascontiguousarray(img, np.float32)
+    h = _lib.default_handle(work.shape[0], work.shape[1])
+    h.blot(work, rects)
+    if work is not img:
+        img[...] = work
+    return img
