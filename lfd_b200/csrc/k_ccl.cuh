@@ -35,11 +35,19 @@ __device__ __forceinline__ u32 ccl_word(const u32* __restrict__ m, int y, int w,
     return kind ? (~v & tail_mask(w, d.W)) : v;
 }
 
+// find with path halving (racy but safe: every store points a node at one of its ancestors)
 __device__ __forceinline__ int uf_find(int* parent, int i)
 {
-    int p;
-    while ((p = __ldcg(&parent[i])) != i) i = p;
-    return i;
+    int cur = __ldcg(&parent[i]);
+    if (cur != i) {
+        int prev = i, next;
+        while (cur > (next = __ldcg(&parent[cur]))) {
+            parent[prev] = next;
+            prev = cur;
+            cur = next;
+        }
+    }
+    return cur;
 }
 
 __device__ __forceinline__ void uf_union(int* parent, int a, int b)
@@ -190,38 +198,66 @@ __device__ __forceinline__ int run_at(const u32* __restrict__ m, const CclBuf& b
     return b.rowbase[y] + b.wpre[(size_t)y * d.WW + w] + __popc(starts & upto) - 1;
 }
 
-// 4. union every run with the runs of the previous row it touches (8- or 4-connectivity)
+// union run `id` of row y with every run of row y-1 it touches (8- or 4-connectivity)
+__device__ __forceinline__ void merge_with_row_above(const u32* __restrict__ m, const CclBuf& b, int y, int id, Dims d, int kind)
+{
+    const int c = kind ? 0 : 1;
+    Run r = b.runs[id];
+    int lo = max((int)r.xs - c, 0), hi = min((int)r.xe + c, d.W - 1);
+    for (int w = lo >> 5; w <= (hi >> 5); w++) {
+        u32 up = ccl_word(m, y - 1, w, d, kind);
+        int blo = max(lo - (w << 5), 0), bhi = min(hi - (w << 5), 31);
+        u32 bits = up & bit_range(blo, bhi);
+        while (bits) {
+            int p = __ffs(bits) - 1;
+            int j = run_at(m, b, y - 1, (w << 5) + p, d, kind);
+            uf_union(b.parent, id, j);
+            // drop the rest of that run inside this word
+            u32 ones = ~up & (0xffffffffu << p);          // first clear bit above p
+            int e = ones ? (__ffs(ones) - 1) : 32;       // run covers bits p .. e-1
+            bits &= (e >= 32) ? 0u : (0xffffffffu << e);
+        }
+    }
+}
+
+#define CCL_BAND 32
+
+// 4a. band-local merge: one CTA walks the rows of a CCL_BAND-row band in order and flattens each row
+//     right after linking it, so union-find trees inside a band never get deeper than a couple of hops
+//     (a frame-wide background component would otherwise build chains as long as the frame is tall).
+__global__ void __launch_bounds__(256)
+k_ccl_merge_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+                 int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    if (ctl[f].nruns[kind] == 0) return;
+    const u32* m = mask + (size_t)f * d.NW;
+    CclBuf b = bufs[f];
+    int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
+    for (int y = y0 + 1; y < y1; y++) {
+        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+        for (int id = r0 + threadIdx.x; id < r1; id += blockDim.x) merge_with_row_above(m, b, y, id, d, kind);
+        __syncthreads();
+        for (int id = r0 + threadIdx.x; id < r1; id += blockDim.x) b.parent[id] = uf_find(b.parent, id);
+        __syncthreads();
+    }
+}
+
+// 4b. stitch the bands: rows y = k * CCL_BAND against row y-1; one warp per boundary row
 __global__ void __launch_bounds__(CCL_WARPS * 32)
 k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
             int pass, Dims d, int kind)
 {
     int f = blockIdx.y;
     if (!ctl[f].active[pass]) return;
-    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
-    if (y >= d.H || y == 0) return;
+    int y = (blockIdx.x * CCL_WARPS + (threadIdx.x >> 5) + 1) * CCL_BAND;
+    if (y >= d.H) return;
     const u32* m = mask + (size_t)f * d.NW;
     CclBuf b = bufs[f];
     if (ctl[f].nruns[kind] == 0) return;
     int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-    const int c = kind ? 0 : 1;
-    for (int id = r0 + lane_id(); id < r1; id += 32) {
-        Run r = b.runs[id];
-        int lo = max((int)r.xs - c, 0), hi = min((int)r.xe + c, d.W - 1);
-        for (int w = lo >> 5; w <= (hi >> 5); w++) {
-            u32 up = ccl_word(m, y - 1, w, d, kind);
-            int blo = max(lo - (w << 5), 0), bhi = min(hi - (w << 5), 31);
-            u32 bits = up & bit_range(blo, bhi);
-            while (bits) {
-                int p = __ffs(bits) - 1;
-                int j = run_at(m, b, y - 1, (w << 5) + p, d, kind);
-                uf_union(b.parent, id, j);
-                // drop the rest of that run inside this word
-                u32 ones = ~up & (0xffffffffu << p);          // first clear bit at or above p
-                int e = ones ? (__ffs(ones) - 1) : 32;       // run covers bits p .. e-1
-                bits &= (e >= 32) ? 0u : (0xffffffffu << e);
-            }
-        }
-    }
+    for (int id = r0 + lane_id(); id < r1; id += 32) merge_with_row_above(m, b, y, id, d, kind);
 }
 
 // 5. flatten + per-component statistics at the root

@@ -26,13 +26,14 @@ static std::string g_create_error;
 
 enum { T_PREP = 0, T_MORPH, T_CANNY, T_CCL_FG, T_CCL_BG, T_RECTS, T_HOUGH, T_CHECK, T_PER_PASS };
 static const char* k_timing_names[] = {
-    "prep(mask+flip+clip+u8+hist)",
+    "setup(memset+star_mask)",
+    "prep(blot+flip+clip+u8+hist)",
     "bright:lut+morph", "bright:sobel+nms", "bright:ccl_fg(hysteresis)", "bright:ccl_bg(holes)",
     "bright:rects+boxfill", "bright:hough", "bright:check_theta",
     "dim:lut+morph", "dim:sobel+nms", "dim:ccl_fg(hysteresis)", "dim:ccl_bg(holes)",
     "dim:rects+boxfill", "dim:hough", "dim:check_theta",
     "results_d2h"};
-#define N_TIMINGS 16
+#define N_TIMINGS 17
 
 struct HoughBufs {
     HoughCfg hc;
@@ -486,9 +487,11 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
     cudaStream_t s = h->stream;
     const bool taps = flags & LFD_KEEP_TAPS;
-    const int tbase = 1 + pass * (T_PER_PASS - 1);   // timing slot of this pass's first stage
+    const int tbase = 2 + pass * (T_PER_PASS - 1);   // event index preceding this pass's first stage
     HoughBufs& hb = h->hb[pass];
     dim3 rows((d.H + CCL_WARPS - 1) / CCL_WARPS, n);
+    const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
+    dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
     k_pass_begin<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, n); LAUNCH_CHECK();
     // LUT + morphology
@@ -517,7 +520,8 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[0], h->ctl, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
     k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_merge<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge_band<<<bands, 256, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->edges[pass], h->ctl, pass, d); LAUNCH_CHECK();
     k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->comp_d, h->ctl, pass, d, 0); LAUNCH_CHECK();
@@ -527,7 +531,8 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[1], h->ctl, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
     k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_merge<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_merge_band<<<bands, 256, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
@@ -579,16 +584,17 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
         clipped = h->clipped;
     }
     const lfd_pass_params& pd = h->params.dim;
+    CK(cudaEventRecord(h->ev[1], s));
     int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 592) pblocks = 592;   // 4 CTAs per SM on 148 SMs
     k_prep<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, h->hist + (size_t)h->B * 256,
                                           clipped, d, mode, (flags & LFD_INPUT_BIGENDIAN) ? 1 : 0, (float)pd.minFlux,
                                           (float)pd.addFlux); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[1], s));
+    CK(cudaEventRecord(h->ev[2], s));
     int rc;
     if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags)) != LFD_OK) return rc; }
-    else for (int i = 2; i <= T_PER_PASS; i++) CK(cudaEventRecord(h->ev[i], s));
+    else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
     if (mode != 1) { if ((rc = run_pass_kernels(h, n, 1, flags)) != LFD_OK) return rc; }
-    else for (int i = T_PER_PASS + 1; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+    else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
     CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));

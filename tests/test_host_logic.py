@@ -1,0 +1,154 @@
+"""CPU tests of the host side: catalog filter, FITS stand-in, path templating, DetectTrails selection logic,
+result decoding, and the C-ABI library's symbols (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lfd_b200
+from lfd_b200 import _lib, fitsio_lite, sdssfiles, synth
+from lfd_b200.removestars import star_rects
+from oracle import ref_pipeline as rp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_abi_library_exports_header_symbols():
+    import __graft_entry__ as ge
+    ge.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = ge.exported_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), s
+    assert L.lfd_abi_version() == 1
+    # struct layout agreed between header and ctypes
+    assert ctypes.sizeof(_lib.PassParams) == 8 * 8 + 8 * 4
+    assert ctypes.sizeof(_lib.Result) == 4 * 3 + 4 * 8 + 8 + 2 * 2 * 16 * 2 * 4
+    assert _lib.RECT_DTYPE.itemsize == 5 * 4 + 3 * 4 + 8 * 4
+
+
+def test_no_gpu_fails_loudly():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(_lib.LfdError):
+        _lib.Handle(64, 64)
+
+
+@pytest.mark.parametrize("flt", list("ugriz"))
+def test_star_rects_match_oracle(flt):
+    for seed in (1, 2, 3):
+        img, cat = synth.make_case("sparse", seed)
+        ref = rp.star_rects(cat, flt, **rp.DEFAULT_REMOVESTARS)
+        a = np.ones(img.shape, np.float32)
+        rp.blot(a, ref)
+        b = np.ones(img.shape, np.float32)
+        for r0, r1, c0, c1 in star_rects(cat, flt, img.shape, **rp.DEFAULT_REMOVESTARS):
+            b[r0:r1, c0:c1] = 0
+        assert np.array_equal(a, b)
+        assert (a == 0).any()
+
+
+def test_star_rects_nan_raises_like_math_ceil():
+    _img, cat = synth.make_case("sparse", 4)
+    cat["ROWC"][3, 2] = np.nan
+    with pytest.raises(ValueError):
+        star_rects(cat, "r", (1489, 2048), **rp.DEFAULT_REMOVESTARS)
+
+
+def test_fitsio_lite_roundtrip(tmp_path):
+    img = np.random.default_rng(0).normal(size=(37, 52)).astype(np.float32)
+    p = str(tmp_path / "a.fits")
+    fitsio_lite.write_image(p, img, dict(synth.DEFAULT_HEADER))
+    assert np.array_equal(fitsio_lite.read(p), img)
+    h = fitsio_lite.read_header(p)
+    assert h["TAI"] == synth.DEFAULT_HEADER["TAI"] and h["NAXIS1"] == 52
+    raw, _ = fitsio_lite.read_raw_image(p)
+    assert np.array_equal(raw.view(">f4").astype(np.float32), img)
+    _img, cat = synth.make_case("sparse", 5)
+    q = str(tmp_path / "b.fits")
+    fitsio_lite.write_bintable(q, cat)
+    data, hdr = fitsio_lite.read(q, header="True")
+    assert hdr["XTENSION"] == "BINTABLE"
+    for k in cat:
+        assert np.array_equal(data[k], cat[k]), k
+
+
+def test_paths_and_runlist(tmp_path):
+    tree = synth.write_sdss_tree(str(tmp_path), 2888, 3, [10], filters=("i",), kinds="empty")
+    lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], str(tmp_path))
+    f = sdssfiles.filename("frame", run=2888, camcol=3, field=10, filter="i")
+    assert f.endswith("frames/301/2888/3/frame-i-002888-3-0010.fits") and os.path.exists(f)
+    o = sdssfiles.filename("photoObj", run=2888, camcol=3, field=10)
+    assert o.endswith("301/2888/3/photoObj-002888-3-0010.fits") and os.path.exists(o)
+    with pytest.raises(ValueError):
+        sdssfiles.filename("frame", run=1, camcol=3, field=10, filter="i")
+
+
+def test_frame_order_matches_reference(tmp_path):
+    g = np.load(os.path.join(GOLD, "golden_run.npz"))
+    tree = synth.write_sdss_tree(str(tmp_path), 2888, 1, [100], filters=("r",), kinds="empty", startfield=100, endfield=103)
+    lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], str(tmp_path))
+    for name, kw in (("run", dict(run=2888)), ("run-camcol", dict(run=2888, camcol=2)),
+                     ("run-filter", dict(run=2888, filter="i")), ("run-camcol-filter", dict(run=2888, camcol=3, filter="z")),
+                     ("camcol-filter", dict(camcol=4, filter="u")), ("camcol-frame", dict(run=2888, camcol=5, field=101)),
+                     ("field", dict(run=2888, camcol=6, filter="g", field=102))):
+        d = lfd_b200.DetectTrails(**kw)
+        assert d._pick == name
+        got = np.array([(r, c, "ugriz".index(f), fl) for r, c, f, fl in d.frame_list()], np.int64).reshape(-1, 4)
+        assert np.array_equal(got, g["order_" + name]), name
+
+
+def test_constructor_quirks():
+    pb, pd, pr = lfd_b200.default_params()
+    d = lfd_b200.DetectTrails(run=1, params_dim={"debug": False, "x": 1})
+    assert d.params_bright == {"debug": False, "x": 1}          # reference bug kept (detecttrails.py:253-254)
+    assert set(d.params_dim) == set(pd) and set(d.params_removestars) == set(pr)
+    with pytest.raises(ValueError):
+        lfd_b200.DetectTrails(camcol=9)
+    with pytest.raises(ValueError):
+        lfd_b200.DetectTrails(run=1, field=3)
+    assert lfd_b200.DetectTrails(run=1, camcol=1, savepath="/x").results == "/x/results.txt"
+
+
+def test_result_decoding():
+    from lfd_b200.processfield import result_from_device
+    r = _lib.Result()
+    r.rect_detection[0] = 0
+    assert result_from_device(r, 0, (1489, 2048)) == (False, None)
+    r.rect_detection[0] = 1
+    r.rejected[0] = 1
+    assert result_from_device(r, 0, (1489, 2048)) == (False, None)
+    r.rejected[0] = 0
+    r.top_equ[0][0][0] = 1180.0
+    r.top_equ[0][0][1] = np.float32(1.0122910)
+    got = result_from_device(r, 0, (1489, 2048))
+    assert got == (True, rp.dictify_hough((1489, 2048), (np.float32(1180.0), np.float32(1.0122910))))
+    r.status = _lib.FRAME_NO_LINES_BOX
+    with pytest.raises(TypeError):
+        result_from_device(r, 0, (1489, 2048))
+
+
+def test_unsupported_params_are_rejected():
+    pb, pd, _ = lfd_b200.default_params()
+    bad = dict(pd, erodeKernel=np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8))
+    with pytest.raises(_lib.UnsupportedParameter):
+        _lib.pass_params(bad, True)
+
+
+def test_check_theta_matches_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n1, n2 = rng.integers(1, 6, 2)
+        h1 = np.stack([rng.integers(-50, 50, n1) * 20.0, rng.integers(0, 180, n1) * np.float32(np.pi / 180)], 1).astype(np.float32).reshape(n1, 1, 2)
+        h2 = np.stack([rng.integers(-50, 50, n2) * 20.0, rng.integers(0, 180, n2) * np.float32(np.pi / 180)], 1).astype(np.float32).reshape(n2, 1, 2)
+        if rng.random() < 0.5:
+            h2[:, 0, :] = h1[:1, 0, :] + rng.normal(0, 0.05, (n2, 2)).astype(np.float32)
+        assert lfd_b200.check_theta(h1, h2, 3, 25, 0.15, 0.15, False) == rp.check_theta(h1, h2, 3, 25, 0.15, 0.15)
