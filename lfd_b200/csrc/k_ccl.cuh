@@ -50,6 +50,15 @@ __device__ __forceinline__ int uf_find(int* parent, int i)
     return cur;
 }
 
+// read-only find: used where the caller then publishes parent[i] = root and later kernels rely on it
+// (a concurrent path-halving store could otherwise replace the root by a mere ancestor)
+__device__ __forceinline__ int uf_find_ro(const int* parent, int i)
+{
+    int p;
+    while ((p = __ldcg(&parent[i])) != i) i = p;
+    return i;
+}
+
 __device__ __forceinline__ void uf_union(int* parent, int a, int b)
 {
     while (true) {
@@ -198,25 +207,36 @@ __device__ __forceinline__ int run_at(const u32* __restrict__ m, const CclBuf& b
     return b.rowbase[y] + b.wpre[(size_t)y * d.WW + w] + __popc(starts & upto) - 1;
 }
 
-// union run `id` of row y with every run of row y-1 it touches (8- or 4-connectivity)
-__device__ __forceinline__ void merge_with_row_above(const u32* __restrict__ m, const CclBuf& b, int y, int id, Dims d, int kind)
+// Linking two adjacent rows.  The overlap graph between the sorted run lists of rows y-1 and y is a
+// staircase: every edge (r below, u above) is either "u is the first run above that r touches" or
+// "r is the first run below that u touches".  So each run does exactly two lookups - first neighbour in
+// the row above, first neighbour in the row below - instead of walking all of its neighbours; a
+// frame-wide background run then costs the same as a one-pixel run.
+__device__ __forceinline__ int first_touching(const u32* __restrict__ m, const CclBuf& b, int yy, Run r, Dims d, int kind)
 {
     const int c = kind ? 0 : 1;
-    Run r = b.runs[id];
     int lo = max((int)r.xs - c, 0), hi = min((int)r.xe + c, d.W - 1);
     for (int w = lo >> 5; w <= (hi >> 5); w++) {
-        u32 up = ccl_word(m, y - 1, w, d, kind);
+        u32 v = ccl_word(m, yy, w, d, kind);
         int blo = max(lo - (w << 5), 0), bhi = min(hi - (w << 5), 31);
-        u32 bits = up & bit_range(blo, bhi);
-        while (bits) {
-            int p = __ffs(bits) - 1;
-            int j = run_at(m, b, y - 1, (w << 5) + p, d, kind);
-            uf_union(b.parent, id, j);
-            // drop the rest of that run inside this word
-            u32 ones = ~up & (0xffffffffu << p);          // first clear bit above p
-            int e = ones ? (__ffs(ones) - 1) : 32;       // run covers bits p .. e-1
-            bits &= (e >= 32) ? 0u : (0xffffffffu << e);
-        }
+        u32 bits = v & bit_range(blo, bhi);
+        if (bits) return run_at(m, b, yy, (w << 5) + __ffs(bits) - 1, d, kind);
+    }
+    return -1;
+}
+
+// link rows y-1 and y: work items [0, n_below) are runs of row y (look up), [n_below, n_below+n_above)
+// are runs of row y-1 (look down)
+__device__ __forceinline__ void link_rows(const u32* __restrict__ m, const CclBuf& b, int y, Dims d, int kind,
+                                          int first, int stride)
+{
+    int a0 = b.rowbase[y - 1], a1 = b.rowbase[y], b1 = b.rowbase[y + 1];
+    int nb = b1 - a1, na = a1 - a0;
+    for (int i = first; i < nb + na; i += stride) {
+        bool below = i < nb;
+        int id = below ? a1 + i : a0 + (i - nb);
+        int j = first_touching(m, b, below ? y - 1 : y, b.runs[id], d, kind);
+        if (j >= 0) uf_union(b.parent, id, j);
     }
 }
 
@@ -236,15 +256,15 @@ k_ccl_merge_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const 
     CclBuf b = bufs[f];
     int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
     for (int y = y0 + 1; y < y1; y++) {
-        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-        for (int id = r0 + threadIdx.x; id < r1; id += blockDim.x) merge_with_row_above(m, b, y, id, d, kind);
+        link_rows(m, b, y, d, kind, threadIdx.x, blockDim.x);
         __syncthreads();
+        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
         for (int id = r0 + threadIdx.x; id < r1; id += blockDim.x) b.parent[id] = uf_find(b.parent, id);
         __syncthreads();
     }
 }
 
-// 4b. stitch the bands: rows y = k * CCL_BAND against row y-1; one warp per boundary row
+// 4b. stitch the bands: rows y = k * CCL_BAND against row y-1; one warp per seam
 __global__ void __launch_bounds__(CCL_WARPS * 32)
 k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
             int pass, Dims d, int kind)
@@ -256,8 +276,7 @@ k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const Frame
     const u32* m = mask + (size_t)f * d.NW;
     CclBuf b = bufs[f];
     if (ctl[f].nruns[kind] == 0) return;
-    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-    for (int id = r0 + lane_id(); id < r1; id += 32) merge_with_row_above(m, b, y, id, d, kind);
+    link_rows(m, b, y, d, kind, lane_id(), 32);
 }
 
 // 5. flatten + per-component statistics at the root
@@ -275,7 +294,7 @@ k_ccl_stats(const u32* __restrict__ strong, CclBuf* __restrict__ bufs, const Fra
     int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
     for (int id = r0 + lane_id(); id < r1; id += 32) {
         Run r = b.runs[id];
-        int root = uf_find(b.parent, id);
+        int root = uf_find_ro(b.parent, id);
         b.parent[id] = root;
         int fl = 0;
         if (kind == 0) {
