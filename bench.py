@@ -231,6 +231,14 @@ def run_ours(args):
     counters = hA.counters()
     value = world * B * args.steps / elapsed
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "profile_only": True,
+                              "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B},
+                              "stages": [{"stage": n, "ms_per_step": ms / args.steps} for n, ms in stage_ms]}))
+        return 0
+
     # ---- e2e: host frames -> device -> results, double-buffered over two handles -------------
     def e2e_loop(steps):
         hs = (hA, hB)
@@ -354,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="device-resident leg only (target command for ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -13,7 +13,7 @@
 #define CANNY_TH 16
 
 __global__ void __launch_bounds__(256)
-k_canny_nms(const u8* __restrict__ img, u32* __restrict__ cand, u32* __restrict__ strong,
+k_canny_nms(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restrict__ cand, u32* __restrict__ strong,
             u8* __restrict__ nms_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int low, int high)
 {
     int f = blockIdx.z;
@@ -23,6 +23,35 @@ k_canny_nms(const u8* __restrict__ img, u32* __restrict__ cand, u32* __restrict_
     __shared__ u16 M[CANNY_TH + 2][CANNY_TW + 4];     // magnitude for rows ty0-1.., cols tx0-1..
     const int tx0 = blockIdx.x * CANNY_TW, ty0 = blockIdx.y * CANNY_TH;
     const u8* src = img + (size_t)f * d.N;
+
+    // A tile whose input window (tile + 2 px) holds no non-zero pixel has zero gradient everywhere:
+    // consult the 1-bit/px non-zero mask the morphology kernel wrote (120 words) instead of loading
+    // 2.6 KB of pixels.  Sky-subtracted frames are mostly such tiles.
+    {
+        int any = 0;
+        if (threadIdx.x < 20 * 6) {
+            int r = threadIdx.x / 6, c = threadIdx.x - r * 6;
+            int y = min(max(ty0 - 2 + r, 0), d.H - 1);
+            int w = (tx0 >> 5) - 1 + c;
+            if (w >= 0 && w < d.WW) any = nz[(size_t)f * d.NW + (size_t)y * d.WW + w] != 0;
+        }
+        if (!__syncthreads_or(any)) {
+            for (int i = threadIdx.x; i < CANNY_TH * (CANNY_TW / 32); i += blockDim.x) {
+                int r = i / (CANNY_TW / 32), c = i - r * (CANNY_TW / 32);
+                int y = ty0 + r, w = (tx0 >> 5) + c;
+                if (y < d.H && w < d.WW) {
+                    size_t o = (size_t)f * d.NW + (size_t)y * d.WW + w;
+                    cand[o] = 0u; strong[o] = 0u;
+                }
+            }
+            if (nms_tap)
+                for (int i = threadIdx.x; i < CANNY_TH * CANNY_TW; i += blockDim.x) {
+                    int y = ty0 + i / CANNY_TW, x = tx0 + i % CANNY_TW;
+                    if (y < d.H && x < d.W) nms_tap[(size_t)f * d.N + (size_t)y * d.W + x] = 0;
+                }
+            return;
+        }
+    }
 
     for (int i = threadIdx.x; i < (CANNY_TH + 4) * (CANNY_TW + 4); i += blockDim.x) {
         int r = i / (CANNY_TW + 4), c = i - r * (CANNY_TW + 4);

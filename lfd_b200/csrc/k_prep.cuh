@@ -66,47 +66,76 @@ k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restric
     const float* src = in + (size_t)f * d.N;
     int quads = d.N >> 2;
     int wq = d.W >> 2;
-    u32 zeros0 = 0, zeros1 = 0;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
-        int y = q / wq, x = (q - y * wq) << 2;
-        int sy = (mode == 0) ? (d.H - 1 - y) : y;
-        float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)sy * d.W + x));
-        if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
-        float a[4] = {v.x, v.y, v.z, v.w};
-        u32 mbits = 0;
-        if (mode == 0) mbits = (mask[(size_t)f * d.NW + (size_t)y * d.WW + (x >> 5)] >> (x & 31)) & 0xf;
-        u32 g0 = 0, g1 = 0;
-        float cl[4];
+    // bins 0..2 hold almost every pixel of a sky-subtracted frame (dim: |v + addFlux| rounds to 1 or 2);
+    // they are counted in registers and merged once per warp, the rest goes to shared-memory atomics
+    u32 z0[3] = {0, 0, 0}, z1[3] = {0, 0, 0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += 2 * stride) {
+        // two independent 16-byte loads in flight per thread
+        float4 vv[2];
+        int qq[2] = {q0, q0 + stride};
+        int yy[2], xx[2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float t = a[k];
-            if (mbits & (1u << k)) t = 0.0f;
-            if (mode != 2) { if (t < 0.0f) t = 0.0f; }          // bright clip (NaN stays NaN)
-            float b = t;
-            if (mode != 1) {
-                if (b < minFlux) b = 0.0f;
-                if (b > 0.0f) b = __fadd_rn(b, addFlux);
+        for (int u = 0; u < 2; u++) {
+            int q = qq[u];
+            if (q < quads) {
+                yy[u] = q / wq; xx[u] = (q - yy[u] * wq) << 2;
+                int sy = (mode == 0) ? (d.H - 1 - yy[u]) : yy[u];
+                vv[u] = __ldcs(reinterpret_cast<const float4*>(src + (size_t)sy * d.W + xx[u]));
             }
-            u32 c0 = csa(t), c1 = csa(b);
-            g0 |= c0 << (8 * k);
-            g1 |= c1 << (8 * k);
-            if (mode != 2) { if (c0) atomicAdd(&sh[0][c0], 1u); else zeros0++; }
-            if (mode != 1) { if (c1) atomicAdd(&sh[1][c1], 1u); else zeros1++; }
-            cl[k] = (mode == 2) ? b : t;
         }
-        size_t o = (size_t)f * d.N + (size_t)y * d.W + x;
-        if (mode != 2) *reinterpret_cast<u32*>(gray0 + o) = g0;
-        if (mode != 1) *reinterpret_cast<u32*>(gray1 + o) = g1;
-        if (clipped) *reinterpret_cast<float4*>(clipped + o) = make_float4(cl[0], cl[1], cl[2], cl[3]);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            int q = qq[u];
+            if (q >= quads) continue;
+            int y = yy[u], x = xx[u];
+            float4 v = vv[u];
+            if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+            float a[4] = {v.x, v.y, v.z, v.w};
+            u32 mbits = 0;
+            if (mode == 0) mbits = (mask[(size_t)f * d.NW + (size_t)y * d.WW + (x >> 5)] >> (x & 31)) & 0xf;
+            u32 g0 = 0, g1 = 0;
+            float cl[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float t = a[k];
+                if (mbits & (1u << k)) t = 0.0f;
+                if (mode != 2) { if (t < 0.0f) t = 0.0f; }          // bright clip (NaN stays NaN)
+                float b = t;
+                if (mode != 1) {
+                    if (b < minFlux) b = 0.0f;
+                    if (b > 0.0f) b = __fadd_rn(b, addFlux);
+                }
+                u32 c0 = csa(t), c1 = csa(b);
+                g0 |= c0 << (8 * k);
+                g1 |= c1 << (8 * k);
+                if (mode != 2) {
+                    if (c0 < 3) { z0[0] += (c0 == 0); z0[1] += (c0 == 1); z0[2] += (c0 == 2); }
+                    else atomicAdd(&sh[0][c0], 1u);
+                }
+                if (mode != 1) {
+                    if (c1 < 3) { z1[0] += (c1 == 0); z1[1] += (c1 == 1); z1[2] += (c1 == 2); }
+                    else atomicAdd(&sh[1][c1], 1u);
+                }
+                cl[k] = (mode == 2) ? b : t;
+            }
+            size_t o = (size_t)f * d.N + (size_t)y * d.W + x;
+            if (mode != 2) *reinterpret_cast<u32*>(gray0 + o) = g0;
+            if (mode != 1) *reinterpret_cast<u32*>(gray1 + o) = g1;
+            if (clipped) *reinterpret_cast<float4*>(clipped + o) = make_float4(cl[0], cl[1], cl[2], cl[3]);
+        }
     }
-    // zero bin: warp-aggregate the dominant value before touching shared memory
-    for (int o = 16; o; o >>= 1) {
-        zeros0 += __shfl_xor_sync(FULLMASK, zeros0, o);
-        zeros1 += __shfl_xor_sync(FULLMASK, zeros1, o);
-    }
-    if (lane_id() == 0) {
-        if (zeros0) atomicAdd(&sh[0][0], zeros0);
-        if (zeros1) atomicAdd(&sh[1][0], zeros1);
+    // low bins: warp-aggregate before touching shared memory
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        for (int o = 16; o; o >>= 1) {
+            z0[k] += __shfl_xor_sync(FULLMASK, z0[k], o);
+            z1[k] += __shfl_xor_sync(FULLMASK, z1[k], o);
+        }
+        if (lane_id() == 0) {
+            if (z0[k]) atomicAdd(&sh[0][k], z0[k]);
+            if (z1[k]) atomicAdd(&sh[1][k], z1[k]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {

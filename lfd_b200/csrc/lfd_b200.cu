@@ -97,7 +97,7 @@ struct lfd_handle {
     int4* rects_h = nullptr;          // pinned
     int* rect_off_h = nullptr;        // pinned
     FrameCtl* ctl_h = nullptr;        // pinned [B]
-    int64_t counters_h[16];
+    int64_t* counters_h = nullptr;    // pinned [16] (a pageable destination would make the D2H copy block the host)
 
     cudaEvent_t ev[N_TIMINGS + 1];
     bool ev_valid[N_TIMINGS + 1];
@@ -296,6 +296,7 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->rects_h) cudaFreeHost(h->rects_h);
     if (h->rect_off_h) cudaFreeHost(h->rect_off_h);
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
+    if (h->counters_h) cudaFreeHost(h->counters_h);
     for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -404,7 +405,8 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     CK(cudaMallocHost((void**)&h->rect_off_h, ((size_t)B + 1) * sizeof(int)));
     CK(cudaMallocHost((void**)&h->ctl_h, (size_t)B * sizeof(FrameCtl)));
     CK(cudaMemset(h->counters_d, 0, 16 * sizeof(int64_t)));
-    memset(h->counters_h, 0, sizeof(h->counters_h));
+    CK(cudaMallocHost((void**)&h->counters_h, 16 * sizeof(int64_t)));
+    memset(h->counters_h, 0, 16 * sizeof(int64_t));
     memset(h->timings, 0, sizeof(h->timings));
     return LFD_OK;
 }
@@ -514,7 +516,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
         ntap = h->nms_tap[pass];
     }
     dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
-    k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255); LAUNCH_CHECK();
+    k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 2], s));
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
@@ -585,7 +587,7 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     }
     const lfd_pass_params& pd = h->params.dim;
     CK(cudaEventRecord(h->ev[1], s));
-    int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 592) pblocks = 592;   // 4 CTAs per SM on 148 SMs
+    int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 1184) pblocks = 1184;   // 8 CTAs of 256 threads per SM on 148 SMs
     k_prep<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, h->hist + (size_t)h->B * 256,
                                           clipped, d, mode, (flags & LFD_INPUT_BIGENDIAN) ? 1 : 0, (float)pd.minFlux,
                                           (float)pd.addFlux); LAUNCH_CHECK();
