@@ -48,13 +48,14 @@ __device__ __forceinline__ float bswapf(float v)
     return __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123));
 }
 
+// ---- generic variant: also emits the clipped float image (standalone pass functions with write-back).
 // mode 0: whole-frame pipeline: mask + flip + bright clip -> gray0 ; + dim threshold/offset -> gray1
 // mode 1: standalone bright on an already flipped frame (no mask, no flip) -> gray0
 // mode 2: standalone dim on an already flipped frame (no bright clip)     -> gray1
 // Each thread converts 4 consecutive pixels (W % 4 == 0).  hist: [2][n][256].
 // clipped (optional): float image after the in-place clip of the selected standalone pass.
 __global__ void __launch_bounds__(256)
-k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0,
+k_prep_generic(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0,
        u8* __restrict__ gray1, u32* __restrict__ hist0, u32* __restrict__ hist1, float* __restrict__ clipped,
        Dims d, int mode, int bigendian, float minFlux, float addFlux)
 {
@@ -141,6 +142,102 @@ k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restric
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         if (mode != 2 && sh[0][i]) atomicAdd(&hist0[(size_t)f * 256 + i], sh[0][i]);
         if (mode != 1 && sh[1][i]) atomicAdd(&hist1[(size_t)f * 256 + i], sh[1][i]);
+    }
+}
+
+
+// ---- fast variant (no clipped output): the instruction-lean kernel of the batch pipeline -----------------
+// saturate_u8(rint(|v|)) in three instructions: fabs (operand modifier), the >= 2^31 / NaN / inf -> 0
+// select, and one cvt.rni.sat.u8.f32 (round-half-even + saturation in hardware; NaN converts to 0).
+__device__ __forceinline__ u32 csa_fast(float v)
+{
+    float a = fabsf(v);
+    a = (a < 2147483648.0f) ? a : 0.0f;
+    u32 r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return r;
+}
+
+// histogram update for four packed u8 values: bins 0..2 (nearly all pixels of a sky-subtracted frame)
+// are counted 4 at a time with SIMD byte compares + popc into registers; anything larger goes to
+// shared-memory atomics.
+__device__ __forceinline__ void hist4(u32 g, u32& n0, u32& n1, u32& n2, u32* sh)
+{
+    n0 += __popc(__vcmpeq4(g, 0x00000000u));
+    n1 += __popc(__vcmpeq4(g, 0x01010101u));
+    n2 += __popc(__vcmpeq4(g, 0x02020202u));
+    u32 big = __vcmpgtu4(g, 0x02020202u);
+    if (big) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 c = (g >> (8 * k)) & 0xffu;
+            if (c > 2) atomicAdd(&sh[c], 1u);
+        }
+    }
+}
+
+// MODE 0: pipeline (mask + flip, both passes) ; 1: bright only ; 2: dim only (no bright clip).
+// One CTA walks whole rows (no integer division); a thread converts 4 px per 16-byte load.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0, u8* __restrict__ gray1,
+       u32* __restrict__ hist0, u32* __restrict__ hist1, Dims d, int bigendian, float minFlux, float addFlux)
+{
+    __shared__ u32 sh[2][256];
+    const int f = blockIdx.y;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const float* src = in + (size_t)f * d.N;
+    const int wq = d.W >> 2;
+    u32 a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;     // popc sums (8 per matching byte)
+    for (int y = blockIdx.x; y < d.H; y += gridDim.x) {
+        const int sy = (MODE == 0) ? (d.H - 1 - y) : y;
+        const float4* srow = reinterpret_cast<const float4*>(src + (size_t)sy * d.W);
+        const u32* mrow = mask + (size_t)f * d.NW + (size_t)y * d.WW;
+        u32* o0 = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)y * d.W);
+        u32* o1 = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)y * d.W);
+        for (int xq = threadIdx.x; xq < wq; xq += blockDim.x) {
+            float4 v = __ldcs(srow + xq);
+            if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+            if (MODE == 0) {
+                u32 mb = (mrow[xq >> 3] >> ((xq & 7) << 2)) & 0xfu;
+                if (mb) {
+                    if (mb & 1u) v.x = 0.0f;
+                    if (mb & 2u) v.y = 0.0f;
+                    if (mb & 4u) v.z = 0.0f;
+                    if (mb & 8u) v.w = 0.0f;
+                }
+            }
+            float t[4] = {v.x, v.y, v.z, v.w};
+            u32 g0 = 0, g1 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float tt = t[k];
+                if (MODE != 2) {
+                    tt = fmaxf(tt, 0.0f);          // v < 0 -> 0 ; NaN -> 0 (the reference keeps NaN, which converts to 0 too)
+                    g0 |= csa_fast(tt) << (8 * k);
+                }
+                if (MODE != 1) {
+                    float b = (tt < minFlux) ? 0.0f : tt;
+                    b = (b > 0.0f) ? __fadd_rn(b, addFlux) : b;
+                    g1 |= csa_fast(b) << (8 * k);
+                }
+            }
+            if (MODE != 2) { o0[xq] = g0; hist4(g0, a0, a1, a2, sh[0]); }
+            if (MODE != 1) { o1[xq] = g1; hist4(g1, b0, b1, b2, sh[1]); }
+        }
+    }
+    u32 acc[6] = {a0, a1, a2, b0, b1, b2};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        u32 vsum = acc[k];
+        for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(FULLMASK, vsum, o);
+        if (lane_id() == 0 && vsum) atomicAdd(&sh[k / 3][k % 3], vsum >> 3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        if (MODE != 2 && sh[0][i]) atomicAdd(&hist0[(size_t)f * 256 + i], sh[0][i]);
+        if (MODE != 1 && sh[1][i]) atomicAdd(&hist1[(size_t)f * 256 + i], sh[1][i]);
     }
 }
 

@@ -587,10 +587,21 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     }
     const lfd_pass_params& pd = h->params.dim;
     CK(cudaEventRecord(h->ev[1], s));
-    int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 1184) pblocks = 1184;   // 8 CTAs of 256 threads per SM on 148 SMs
-    k_prep<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, h->hist + (size_t)h->B * 256,
-                                          clipped, d, mode, (flags & LFD_INPUT_BIGENDIAN) ? 1 : 0, (float)pd.minFlux,
-                                          (float)pd.addFlux); LAUNCH_CHECK();
+    const int be = (flags & LFD_INPUT_BIGENDIAN) ? 1 : 0;
+    u32* hist1 = h->hist + (size_t)h->B * 256;
+    if (clipped) {
+        int pblocks = (d.N / 4 + 255) / 256; if (pblocks > 1184) pblocks = 1184;
+        k_prep_generic<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, clipped, d, mode, be,
+                                                      (float)pd.minFlux, (float)pd.addFlux); LAUNCH_CHECK();
+    } else {
+        // whole rows per CTA; 148 SMs x 8 CTAs of 256 threads, spread over the frames of the batch
+        int rb = (1184 + n - 1) / n; if (rb < 8) rb = 8; if (rb > d.H) rb = d.H;
+        dim3 pg(rb, n);
+        if (mode == 0) k_prep<0><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
+        else if (mode == 1) k_prep<1><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
+        else k_prep<2><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
+        LAUNCH_CHECK();
+    }
     CK(cudaEventRecord(h->ev[2], s));
     int rc;
     if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags)) != LFD_OK) return rc; }
