@@ -152,3 +152,201 @@ k_morph(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict_
         }
     }
 }
+
+// ================================================================================================
+// Register-marching variant (the production path for the kernel shapes instantiated below).
+//
+// A warp owns a strip of 64 4-pixel words (256 px: 224 useful + 16 px of halo per side) and marches
+// down MARCH_R output rows.  Each lane holds 8 consecutive pixels of the current row as four u16x2
+// registers, so every min/max is a native VIMNMX3.U16x2 (byte-wise __vmaxu4 is emulated with 7 ALU
+// ops on sm_100a, the 16x2 three-input form is one).  Horizontal windows take neighbour pixels with
+// warp shuffles, vertical windows are register rings indexed at compile time (the row loop is
+// unrolled by lcm(EH, DH)), so the image is read once from global memory and nothing is staged in
+// shared memory except the 256-byte LUT.
+// ================================================================================================
+#define MARCH_R 64            // output rows per warp
+#define MARCH_UW 56           // useful words per strip (7 mask words)
+#define MARCH_HW 4            // halo words per side (lanes 0,1 and 30,31)
+
+template <bool IS_MAX> __device__ __forceinline__ u32 mm2(u32 a, u32 b) { return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b); }
+template <bool IS_MAX> __device__ __forceinline__ u32 mm3(u32 a, u32 b, u32 c)
+{
+    return IS_MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
+}
+
+// out pixel x = op over pixels x+LO .. x+HI of the row; p[i] = (px 2i, px 2i+1) of the lane's 8 pixels
+template <bool IS_MAX, int LO, int HI>
+__device__ __forceinline__ void hwin16(const u32 (&p)[4], u32 (&out)[4])
+{
+    constexpr int KL = (-LO + 1) / 2, KR = (HI + 1) / 2, NE = KL + 4 + KR;
+    static_assert(KL <= 4 && KR <= 4, "horizontal reach exceeds one lane (8 px)");
+    if (LO == 0 && HI == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = p[i];
+        return;
+    }
+    u32 E[NE];
+#pragma unroll
+    for (int i = 0; i < 4; i++) E[KL + i] = p[i];
+#pragma unroll
+    for (int j = 0; j < KL; j++) E[KL - 1 - j] = __shfl_up_sync(FULLMASK, p[3 - j], 1);
+#pragma unroll
+    for (int j = 0; j < KR; j++) E[KL + 4 + j] = __shfl_down_sync(FULLMASK, p[j], 1);
+    u32 S[NE];      // S[j] = (px 2j+1, px 2j+2) of the extended row
+#pragma unroll
+    for (int j = 0; j + 1 < NE; j++) S[j] = __byte_perm(E[j], E[j + 1], 0x5432);
+    S[NE - 1] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // term for offset o: even -> E[KL + i + o/2], odd -> S[KL + i + (o-1)/2]
+        u32 acc = 0;
+        bool first = true;
+        u32 pend = 0;
+        bool have_pend = false;
+#pragma unroll
+        for (int o = LO; o <= HI; o++) {
+            int fl = (o >= 0) ? (o >> 1) : -((-o + 1) >> 1);        // floor(o / 2)
+            u32 t = (o & 1) ? S[KL + i + fl] : E[KL + i + fl];
+            if (first) { acc = t; first = false; }
+            else if (!have_pend) { pend = t; have_pend = true; }
+            else { acc = mm3<IS_MAX>(acc, pend, t); have_pend = false; }
+        }
+        if (have_pend) acc = mm2<IS_MAX>(acc, pend);
+        out[i] = acc;
+    }
+}
+
+template <bool IS_MAX, int K>
+__device__ __forceinline__ u32 vreduce16(const u32 (&r)[K][4], int c)
+{
+    u32 acc = r[0][c];
+    int k = 1;
+#pragma unroll
+    for (; k + 1 < K; k += 2) acc = mm3<IS_MAX>(acc, r[k][c], r[k + 1][c]);
+    if (k < K) acc = mm2<IS_MAX>(acc, r[k][c]);
+    return acc;
+}
+
+__host__ __device__ constexpr int morph_gcd(int a, int b) { return b == 0 ? a : morph_gcd(b, a % b); }
+
+// four u16x2 pairs -> LUT -> two packed 4-pixel words
+__device__ __forceinline__ void lut_pack(const u32 (&o)[4], const u8* slut, u32& w0, u32& w1)
+{
+    u32 r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = (u32)slut[o[i] & 0xffffu] | ((u32)slut[o[i] >> 16] << 16);
+    w0 = __byte_perm(r[0], r[1], 0x6420);
+    w1 = __byte_perm(r[2], r[3], 0x6420);
+}
+
+// bit k = byte k of w is non-zero
+__device__ __forceinline__ u32 nzbits4(u32 w)
+{
+    u32 m = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+    return ((m >> 7) * 0x10204080u) >> 28;
+}
+
+template <int EH, int EW, int DH, int DW>
+__global__ void __launch_bounds__(128)
+k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict__ morph, u32* __restrict__ nz,
+              u8* __restrict__ eroded_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int nstrips, int nunits)
+{
+    const int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    __shared__ u8 slut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) slut[i] = lut[(size_t)f * 256 + i];
+    __syncthreads();
+    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= nunits) return;
+    const int chunk = unit / nstrips, s = unit - chunk * nstrips;
+    constexpr bool HAS_E = EH > 0;
+    constexpr int EHR = HAS_E ? EH : 1;
+    constexpr int E_T = HAS_E ? -(EH / 2) : 0, E_B = HAS_E ? EH - 1 - EH / 2 : 0;
+    constexpr int E_L = HAS_E ? -(EW / 2) : 0, E_R = HAS_E ? EW - 1 - EW / 2 : 0;
+    constexpr int D_T = -(DH / 2), D_B = DH - 1 - DH / 2, D_L = -(DW / 2), D_R = DW - 1 - DW / 2;
+    constexpr int U = EHR * DH / morph_gcd(EHR, DH);
+    const int lane = lane_id();
+    const int Ww = d.W >> 2;
+    const int wx = s * MARCH_UW - MARCH_HW + 2 * lane;       // first of this lane's two words (even)
+    const bool col_in = wx >= 0 && wx < Ww;
+    const bool lane_out = lane >= 2 && lane < 30 && col_in;
+    const int y0 = chunk * MARCH_R, y1 = min(y0 + MARCH_R, d.H);
+    const int yfirst = y0 + D_T + E_T, ylast = y1 - 1 + D_B + E_B;
+    const uint2* g = reinterpret_cast<const uint2*>(gray + (size_t)f * d.N);
+    uint2* mo = reinterpret_cast<uint2*>(morph + (size_t)f * d.N);
+    uint2* et = eroded_tap ? reinterpret_cast<uint2*>(eroded_tap + (size_t)f * d.N) : nullptr;
+    const u32 lut0 = slut[0];
+    // mask word of this lane's group: lanes 2..5 -> word 7s, 6..9 -> 7s+1, ...
+    const int r = (lane - 2) & 31;
+    const int mw = s * (MARCH_UW / 8) + (r >> 2);
+    const int q8 = (r & 3) * 8;
+    const int src1 = ((r ^ 1) + 2) & 31, src2 = ((r ^ 2) + 2) & 31;
+    u32 eR[EHR][4], dR[DH][4];
+#pragma unroll
+    for (int k = 0; k < EHR; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) eR[k][c] = 0;
+#pragma unroll
+    for (int k = 0; k < DH; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) dR[k][c] = 0;
+
+    for (int yb = yfirst; yb <= ylast; yb += U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int y = yb + u;
+            uint2 v = HAS_E ? make_uint2(0xffffffffu, 0xffffffffu) : make_uint2(0u, 0u);
+            const bool rin = y >= 0 && y < d.H;
+            if (rin && col_in) v = __ldg(g + (((size_t)y * Ww + wx) >> 1));
+            u32 p[4];
+            if (HAS_E && !(rin && col_in)) {
+                p[0] = p[1] = p[2] = p[3] = 0xffffffffu;
+            } else {
+                p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
+                p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
+            }
+            u32 e[4];
+            int ye = y;
+            if (HAS_E) {
+                u32 hm[4];
+                hwin16<false, E_L, E_R>(p, hm);
+#pragma unroll
+                for (int c = 0; c < 4; c++) eR[u % EHR][c] = hm[c];
+                ye = y - E_B;
+                const bool ein = col_in && ye >= 0 && ye < d.H;
+#pragma unroll
+                for (int c = 0; c < 4; c++) e[c] = ein ? vreduce16<false, EHR>(eR, c) : 0u;
+                if (et && ye >= y0 && ye < y1) {
+                    u32 w0, w1;
+                    lut_pack(e, slut, w0, w1);
+                    if (lane_out) et[((size_t)ye * Ww + wx) >> 1] = make_uint2(w0, w1);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) e[c] = p[c];
+            }
+            u32 hd[4];
+            hwin16<true, D_L, D_R>(e, hd);
+#pragma unroll
+            for (int c = 0; c < 4; c++) dR[u % DH][c] = hd[c];
+            const int yo = ye - D_B;
+            if (yo >= y0 && yo < y1) {                       // warp-uniform
+                u32 o[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) o[c] = vreduce16<true, DH>(dR, c);
+                u32 w0 = 0, w1 = 0;
+                const bool anynz = __any_sync(FULLMASK, (o[0] | o[1] | o[2] | o[3]) != 0u);
+                if (anynz || lut0 != 0u) lut_pack(o, slut, w0, w1);
+                if (!lane_out) { w0 = 0; w1 = 0; }
+                if (lane_out) mo[((size_t)yo * Ww + wx) >> 1] = make_uint2(w0, w1);
+                u32 bits = 0;
+                if (anynz || lut0 != 0u) {
+                    bits = (nzbits4(w0) | (nzbits4(w1) << 4)) << q8;
+                    bits |= __shfl_sync(FULLMASK, bits, src1);
+                    bits |= __shfl_sync(FULLMASK, bits, src2);
+                }
+                if ((r & 3) == 0 && lane >= 2 && lane < 30 && mw < d.WW) nz[(size_t)f * d.NW + (size_t)yo * d.WW + mw] = bits;
+            }
+        }
+    }
+}

@@ -267,8 +267,8 @@ static int hough_setup(lfd_handle* h, HoughBufs* hb, int H, int W, double rho_, 
     CK(cudaMemcpyAsync(hb->tabSin, ts.data(), hc.numangle * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(hb->tabCos, tc.data(), hc.numangle * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (hb->smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_hough_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb->smem));
+    // the limit is per function, not per launch: both passes (and lfd_hough_lines) share k_hough_vote
+    CK(cudaFuncSetAttribute(k_hough_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
     return LFD_OK;
 }
 
@@ -505,9 +505,30 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
         if (!h->eroded_tap) { int rc = dev_alloc(h, &h->eroded_tap, (size_t)h->B * d.N); if (rc) return rc; }
         etap = h->eroded_tap;
     }
-    dim3 mg((d.W + MORPH_TW - 1) / MORPH_TW, (d.H + MORPH_TH - 1) / MORPH_TH, n);
-    k_morph<<<mg, 256, 0, s>>>(h->gray[pass], h->lut + (size_t)pass * h->B * 256, h->morph[pass], h->nz[pass], etap,
-                              h->ctl, pass, d, mc); LAUNCH_CHECK();
+    {
+        const u8* lutp = h->lut + (size_t)pass * h->B * 256;
+        const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + MARCH_R - 1) / MARCH_R;
+        const int nunits = nstrips * nchunks;
+        dim3 gg((nunits + 3) / 4, n);
+        bool done = false;
+#define MORPH_CASE(EH_, EW_, DH_, DW_)                                                                              \
+        if (!done && (d.W % 8) == 0 && mc.eh == EH_ && mc.ew == EW_ && mc.dh == DH_ && mc.dw == DW_) {                \
+            k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, \
+                                                               h->ctl, pass, d, nstrips, nunits);                    \
+            done = true;                                                                                             \
+        }
+        MORPH_CASE(0, 0, 4, 4)      // params_bright default (detecttrails.py:204)
+        MORPH_CASE(3, 3, 9, 9)      // params_dim default (detecttrails.py:220-221)
+        MORPH_CASE(3, 3, 15, 15)    // high-sensitivity dim (BASELINE.json config 4)
+        MORPH_CASE(0, 0, 9, 9)
+        MORPH_CASE(0, 0, 3, 3)
+#undef MORPH_CASE
+        if (!done) {                // any other all-ones rectangle: shared-memory tile kernel
+            dim3 mg((d.W + MORPH_TW - 1) / MORPH_TW, (d.H + MORPH_TH - 1) / MORPH_TH, n);
+            k_morph<<<mg, 256, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, h->ctl, pass, d, mc);
+        }
+        LAUNCH_CHECK();
+    }
     CK(cudaEventRecord(h->ev[tbase + 1], s));
     // Sobel + NMS
     u8* ntap = nullptr;
