@@ -54,46 +54,101 @@ def make_pool(n, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every few ms DURING the timed regions (NVML in a thread; the
+    B200_PROFILING.md nvidia-smi query is the fallback).  pause()/resume() bracket untimed sections."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, gpu):
-        self.gpu, self.p, self.f = gpu, None, None
+    def __init__(self, gpu, period_s=0.004):
+        import threading
+        self.gpu, self.period = gpu, period_s
+        self.sm, self.bits, self.smax = [], 0, None
+        self._run = threading.Event()
+        self._stop = threading.Event()
+        self._th = None
+        self._nv = None
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            dev = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu).uuid)
+                dev = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                dev = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self._nv, self._dev = pynvml, dev
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv, dev = self._nv, self._dev
+        while not self._stop.is_set():
+            if self._run.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)))
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(dev))
+                except Exception:
+                    pass
+            time.sleep(self.period)
 
     def start(self):
+        import threading
+        if self._nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+        else:
+            self._smi_start()
+        self.resume()
+
+    def resume(self):
+        self._run.set()
+
+    def pause(self):
+        self._run.clear()
+
+    # nvidia-smi fallback (one process for the whole run; coarse)
+    def _smi_start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self._f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self._p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                        "-lms", "20"], stdout=self._f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
-            self.p = None
+            self._p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.p:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f:
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 9:
-                continue
+        self._stop.set()
+        self.pause()
+        if self._th is not None:
+            self._th.join(timeout=2)
+        elif getattr(self, "_p", None):
+            self._p.terminate()
             try:
-                sm.append(float(t[1])); smax.append(float(t[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+                self._p.wait(timeout=5)
+            except Exception:
+                self._p.kill()
+            self._f.flush(); self._f.seek(0)
+            for line in self._f:
+                t = [x.strip() for x in line.split(",")]
+                try:
+                    self.sm.append(float(t[0])); self.smax = float(t[1])
+                except (ValueError, IndexError):
+                    continue
+                for (bit, _), v in zip(self.REASONS[:4], t[2:6]):
+                    if v.lower().startswith("active"):
+                        self.bits |= bit
+            os.unlink(self._f.name)
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [n for b, n in self.REASONS if self.bits & b],
+               "samples": len(self.sm), "source": self.source}
+        if self.sm:
+            out["sm_mhz"] = statistics.median(self.sm)
+            out["sm_min_mhz"] = min(self.sm)
         return out
 
 
@@ -214,20 +269,21 @@ def run_ours(args):
     sampler.start()
     l0 = hA.kernel_launches()
     t0 = time.perf_counter()
-    dev_ms = 0.0
+    hA.timer_mark(0)
     for _ in range(args.steps):
         hA.run_resident(B); hA.wait()
         tm = hA.timings()
-        dev_ms += sum(ms for _, ms in tm)
         stage_ms = tm if stage_ms is None else [(n, a + b) for (n, a), (_, b) in zip(stage_ms, tm)]
+    hA.timer_mark(1)
+    dev_ms = hA.timer_elapsed_ms(0, hA, 1)            # CUDA events on the library's stream, first launch -> last result
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
-    elapsed = time.perf_counter() - t0
+    wall_s = time.perf_counter() - t0
+    sampler.pause()
     launches = hA.kernel_launches() - l0
-    clocks = sampler.stop()
-    elapsed = reduce_max(elapsed)
-    dev_ms = reduce_max(dev_ms)
+    elapsed = reduce_max(dev_ms) / 1e3
+    wall_s = reduce_max(wall_s)
     counters = hA.counters()
     value = world * B * args.steps / elapsed
 
@@ -250,12 +306,19 @@ def run_ours(args):
     e2e_loop(max(args.warmup, 2))
     barrier()
     l1 = hA.kernel_launches() + hB.kernel_launches()
+    sampler.resume()
     t0 = time.perf_counter()
+    hA.timer_mark(2)
     e2e_loop(args.steps)
+    last = (hA, hB)[(args.steps - 1) & 1]
+    last.timer_mark(3)
+    e2e_dev_ms = hA.timer_elapsed_ms(2, last, 3)      # device clock: first H2D enqueued -> last result copied back
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
-    e2e_elapsed = reduce_max(time.perf_counter() - t0)
+    e2e_wall = reduce_max(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    e2e_elapsed = reduce_max(e2e_dev_ms) / 1e3
     launches_e2e = hA.kernel_launches() + hB.kernel_launches() - l1
     e2e_value = world * B * args.steps / e2e_elapsed
     # H2D-only time (PCIe) reported separately
@@ -335,7 +398,8 @@ def run_ours(args):
                    "(sparse/dense/trail/satellite mix, seeded), inputs %.0f MB per step > L2 (126 MB), no L2 flush" % (B * N * 4 / 1e6),
                    "kinds": {k: kinds.count(k) for k in sorted(set(kinds))}, "detections_per_batch": int(n_detect),
                    "parallelism": "frame-sharded x%d, no collective" % world},
-        "device_ms_per_step": dev_ms / args.steps,
+        "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside: "
+                  "%.3f ms/step resident, %.3f ms/step e2e" % (1e3 * wall_s / args.steps, 1e3 * e2e_wall / args.steps),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_elapsed / args.steps, "h2d_only_ms_per_step": 1e3 * h2d_s,
@@ -358,7 +422,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

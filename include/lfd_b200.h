@@ -192,6 +192,10 @@ int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, do
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
 const char* lfd_timing_name(int i);
+/* Benchmark timing on the device: record a CUDA event (slot 0..3) on the handle's stream; elapsed ms between a
+ * mark of `h` and a mark of `h_end` (may be the same handle; both must belong to the same GPU). */
+int lfd_timer_mark(lfd_handle* h, int slot);
+int lfd_timer_elapsed(lfd_handle* h, int slot_start, lfd_handle* h_end, int slot_end, float* ms);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lfd_kernel_launches(const lfd_handle* h);
 /* Work counters of the last run, summed over the batch: [0] nonzero px voted equ, [1] box, [2] votes,

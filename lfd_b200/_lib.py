@@ -116,6 +116,8 @@ def lib():
                                       ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
         L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.lfd_timer_elapsed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         if L.lfd_abi_version() != 1:
             raise ImportError("liblfd_b200.so ABI mismatch")
         _lib = L
@@ -315,6 +317,16 @@ class Handle:
         names = ["nnz_equ", "nnz_box", "votes", "runs_fg", "runs_bg", "contours", "passing_rects", "frames_dim",
                  "frames_hough", "frames_bright_run", "frames_dim_run"]
         return {k: int(c[i]) for i, k in enumerate(names)}
+
+    def timer_mark(self, slot):
+        """Record a CUDA event on this handle's stream (device-side benchmark timing)."""
+        self._ck(self._L.lfd_timer_mark(self.h, slot))
+
+    def timer_elapsed_ms(self, slot_start, end_handle=None, slot_end=1):
+        ms = ctypes.c_float()
+        eh = self if end_handle is None else end_handle
+        self._ck(self._L.lfd_timer_elapsed(self.h, slot_start, eh.h, slot_end, ctypes.byref(ms)))
+        return float(ms.value)
 
     def kernel_launches(self):
         return int(self._L.lfd_kernel_launches(self.h))

@@ -264,6 +264,116 @@ k_ccl_merge_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const 
     }
 }
 
+// ---- shared-memory union-find (band-local): same algorithm as uf_find / uf_union on a __shared__ array
+__device__ __forceinline__ int suf_find(volatile int* p, int i)
+{
+    int cur = p[i];
+    if (cur != i) {
+        int prev = i, next;
+        while (cur > (next = p[cur])) {
+            p[prev] = next;
+            prev = cur;
+            cur = next;
+        }
+    }
+    return cur;
+}
+
+__device__ __forceinline__ void suf_union(int* p, int a, int b)
+{
+    while (true) {
+        a = suf_find(p, a);
+        b = suf_find(p, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&p[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+#define CCL_BAND_CAP 3584          // runs of one band kept in shared memory (12 B each = 42 KB)
+
+// 3+4a fused: materialise the runs of a CCL_BAND-row band, link all of its row pairs at once with a
+// union-find that lives in shared memory, and publish band-local roots.  Run ids are raster-ordered, so
+// a band's runs are the contiguous range [rowbase[y0], rowbase[y1]) and local index = id - rowbase[y0].
+// Bands with more runs than CCL_BAND_CAP use the global parent array with the same code path.
+__global__ void __launch_bounds__(256)
+k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+           int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    if (ctl[f].nruns[kind] == 0) return;
+    const u32* m = mask + (size_t)f * d.NW;
+    CclBuf b = bufs[f];
+    const int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
+    const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
+    if (nb == 0) return;
+    __shared__ int sp[CCL_BAND_CAP];
+    __shared__ Run srun[CCL_BAND_CAP];
+    const bool insm = nb <= CCL_BAND_CAP;
+    // fill: one warp per row, rows strided over the 8 warps
+    for (int y = y0 + (threadIdx.x >> 5); y < y1; y += 8) {
+        int rb = b.rowbase[y];
+        for (int w = lane_id(); w < d.WW; w += 32) {
+            u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
+            u32 starts = cur & ~((cur << 1) | (prev >> 31));
+            int id = rb + b.wpre[(size_t)y * d.WW + w];
+            while (starts) {
+                int s = __ffs(starts) - 1;
+                starts &= starts - 1;
+                u32 above = ~(cur >> s);
+                int t = above ? (__ffs(above) - 1) : 32;
+                int xe;
+                if (s + t < 32) {
+                    xe = (w << 5) + s + t - 1;
+                } else {
+                    xe = (w << 5) + 31;
+                    for (int w2 = w + 1; w2 < d.WW; w2++) {
+                        u32 nx = ~ccl_word(m, y, w2, d, kind);
+                        int t2 = nx ? (__ffs(nx) - 1) : 32;
+                        xe = (w2 << 5) + t2 - 1;
+                        if (t2 < 32) break;
+                    }
+                }
+                Run r; r.xs = (u16)((w << 5) + s); r.xe = (u16)xe; r.y = (u16)y; r.pad = 0;
+                b.runs[id] = r;
+                b.flag[id] = 0;
+                b.ymax[id] = y;
+                b.compidx[id] = -1;
+                if (insm) { srun[id - base] = r; sp[id - base] = id - base; }
+                else b.parent[id] = id;
+                id++;
+            }
+        }
+    }
+    __syncthreads();
+    // link every run with the first run it touches in the row above and in the row below (staircase argument)
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        Run r = insm ? srun[i] : b.runs[base + i];
+        if ((int)r.y > y0) {
+            int j = first_touching(m, b, r.y - 1, r, d, kind);
+            if (j >= 0) { if (insm) suf_union(sp, i, j - base); else uf_union(b.parent, base + i, j); }
+        }
+        if ((int)r.y + 1 < y1) {
+            int j = first_touching(m, b, r.y + 1, r, d, kind);
+            if (j >= 0) { if (insm) suf_union(sp, i, j - base); else uf_union(b.parent, base + i, j); }
+        }
+    }
+    __syncthreads();
+    if (insm) {
+        volatile int* vp = sp;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            int r = i, pr;
+            while ((pr = vp[r]) != r) r = pr;
+            b.parent[base + i] = base + r;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) b.parent[base + i] = uf_find_ro(b.parent, base + i);
+    }
+}
+
 // 4b. stitch the bands: rows y = k * CCL_BAND against row y-1; one warp per seam
 __global__ void __launch_bounds__(CCL_WARPS * 32)
 k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,

@@ -102,6 +102,8 @@ struct lfd_handle {
     cudaEvent_t ev[N_TIMINGS + 1];
     bool ev_valid[N_TIMINGS + 1];
     float timings[N_TIMINGS];
+    cudaEvent_t mark[4];              // caller-placed timestamps on the handle's stream (lfd_timer_mark)
+    bool mark_valid[4];
 };
 
 #define CK(call)                                                                                   \
@@ -298,6 +300,7 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
     if (h->counters_h) cudaFreeHost(h->counters_h);
     for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 4; i++) if (h->mark_valid[i]) cudaEventDestroy(h->mark[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return LFD_OK;
@@ -325,6 +328,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
+    for (int i = 0; i < 4; i++) { CK(cudaEventCreate(&h->mark[i])); h->mark_valid[i] = true; }
 
     const int B = h->B;
     const size_t N = h->d.N, NW = h->d.NW;
@@ -417,6 +421,7 @@ extern "C" int lfd_create_ex(int device, int max_batch, int height, int width, c
     *out = nullptr;
     lfd_handle* h = new lfd_handle();
     memset(h->ev_valid, 0, sizeof(h->ev_valid));
+    memset(h->mark_valid, 0, sizeof(h->mark_valid));
     int rc = create_impl(h, device, max_batch, height, width, cfg);
     if (rc != LFD_OK) {
         g_create_error = h->err;
@@ -542,8 +547,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[0], h->ctl, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_merge_band<<<bands, 256, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->edges[pass], h->ctl, pass, d); LAUNCH_CHECK();
@@ -553,8 +557,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     // background runs: hole contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[1], h->ctl, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_fill<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_merge_band<<<bands, 256, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
@@ -915,6 +918,25 @@ extern "C" int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n
     int n = N_TIMINGS < max_entries ? N_TIMINGS : max_entries;
     for (int i = 0; i < n; i++) ms[i] = h->timings[i];
     if (n_entries) *n_entries = n;
+    return LFD_OK;
+}
+
+// caller-placed CUDA-event timestamps on the handle's stream (benchmark timing on the device)
+extern "C" int lfd_timer_mark(lfd_handle* h, int slot)
+{
+    if (!h || slot < 0 || slot >= 4) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    CK(cudaEventRecord(h->mark[slot], h->stream));
+    return LFD_OK;
+}
+
+extern "C" int lfd_timer_elapsed(lfd_handle* h, int slot_start, lfd_handle* h_end, int slot_end, float* ms)
+{
+    if (!h || !h_end || !ms || slot_start < 0 || slot_start >= 4 || slot_end < 0 || slot_end >= 4) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    CK(cudaEventSynchronize(h->mark[slot_start]));
+    CK(cudaEventSynchronize(h_end->mark[slot_end]));
+    CK(cudaEventElapsedTime(ms, h->mark[slot_start], h_end->mark[slot_end]));
     return LFD_OK;
 }
 
