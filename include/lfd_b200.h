@@ -192,6 +192,9 @@ int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, do
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
 const char* lfd_timing_name(int i);
+/* Developer aid: with LFD_KTIMING=1 in the environment at lfd_create time every launch is followed by a CUDA
+ * event; returns (source line in lfd_b200.cu, ms) per launch of the last run. */
+int lfd_get_ktimings(lfd_handle* h, int* lines, float* ms, int max_entries, int* n_entries);
 /* Benchmark timing on the device: record a CUDA event (slot 0..3) on the handle's stream; elapsed ms between a
  * mark of `h` and a mark of `h_end` (may be the same handle; both must belong to the same GPU). */
 int lfd_timer_mark(lfd_handle* h, int slot);

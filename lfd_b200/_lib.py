@@ -328,6 +328,14 @@ class Handle:
         self._ck(self._L.lfd_timer_elapsed(self.h, slot_start, eh.h, slot_end, ctypes.byref(ms)))
         return float(ms.value)
 
+    def ktimings(self):
+        """[(source line, ms)] per launch of the last run (only with LFD_KTIMING=1)."""
+        lines = (ctypes.c_int * 1024)()
+        ms = (ctypes.c_float * 1024)()
+        n = ctypes.c_int()
+        self._ck(self._L.lfd_get_ktimings(self.h, lines, ms, 1024, ctypes.byref(n)))
+        return [(int(lines[i]), float(ms[i])) for i in range(n.value)]
+
     def kernel_launches(self):
         return int(self._L.lfd_kernel_launches(self.h))
 

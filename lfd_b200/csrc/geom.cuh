@@ -80,39 +80,14 @@ LFD_HD void normalise_angle(double ang, float w, float h, Rect* r)
     r->w = w; r->h = h; r->angle = (float)ang;
 }
 
-// cv2.minAreaRect of a strict convex hull st[0..n) taken in the order start, start+1, ... (mod n).
-// vect/inv scratch: 2n and n floats.
-LFD_HD void min_area_rect(const Pt* st, int n, int start, float* vect, float* inv, Rect* out)
+// Rotating calipers of cv2.minAreaRect (4.13) on a strict convex hull of n >= 3 vertices.  `hp(i)` returns
+// vertex i (0 <= i < n) in caliper order; vect[2i..2i+1] = edge i -> i+1 as floats, inv[i] = 1/|edge i|;
+// left/bottom/right/top = FIRST index of min x / min y / max x / max y (cv2 scans with strict compares).
+template <class HP>
+LFD_HD void min_area_rect_core(const HP& hp, int n, const float* vect, const float* inv, int left, int bottom,
+                               int right, int top, Rect* out)
 {
     const double RAD2DEG = 180.0 / 3.14159265358979323846;
-    out->cx = out->cy = out->w = out->h = out->angle = 0.f;
-    if (n <= 0) return;
-#define HP(i) st[((i) + start) % n]
-    if (n == 1) { out->cx = (float)st[0].x; out->cy = (float)st[0].y; out->angle = -90.f; return; }
-    if (n == 2) {
-        Pt a = HP(0), b = HP(1);
-        out->cx = ((float)a.x + (float)b.x) * 0.5f;
-        out->cy = ((float)a.y + (float)b.y) * 0.5f;
-        double dx = (double)((float)b.x - (float)a.x), dy = (double)((float)b.y - (float)a.y);
-        float w = (float)sqrt(dx * dx + dy * dy);
-        normalise_angle(atan2(dy, dx) * RAD2DEG, w, 0.f, out);
-        return;
-    }
-    int left = 0, bottom = 0, right = 0, top = 0;
-    float p0x = (float)HP(0).x, p0y = (float)HP(0).y;
-    float left_x = p0x, right_x = p0x, top_y = p0y, bottom_y = p0y;
-    for (int i = 0; i < n; i++) {
-        if (p0x < left_x) { left_x = p0x; left = i; }
-        if (p0x > right_x) { right_x = p0x; right = i; }
-        if (p0y > top_y) { top_y = p0y; top = i; }
-        if (p0y < bottom_y) { bottom_y = p0y; bottom = i; }
-        Pt q = HP(i + 1 < n ? i + 1 : 0);
-        float px = (float)q.x, py = (float)q.y;
-        double dx = (double)(px - p0x), dy = (double)(py - p0y);
-        vect[2 * i] = (float)dx; vect[2 * i + 1] = (float)dy;
-        inv[i] = (float)(1. / sqrt(dx * dx + dy * dy));
-        p0x = px; p0y = py;
-    }
     float orientation = 0.f;
     {
         double ax = vect[2 * (n - 1)], ay = vect[2 * (n - 1) + 1];
@@ -149,17 +124,19 @@ LFD_HD void min_area_rect(const Pt* st, int n, int start, float* vect, float* in
         default: base_a = -ly; base_b = lx; break;
         }
         seq[me] += 1; if (seq[me] == n) seq[me] = 0;
-        float dx = (float)HP(seq[1]).x - (float)HP(seq[3]).x, dy = (float)HP(seq[1]).y - (float)HP(seq[3]).y;
+        Pt q1 = hp(seq[1]), q3 = hp(seq[3]), q2 = hp(seq[2]), q0 = hp(seq[0]);
+        float dx = (float)q1.x - (float)q3.x, dy = (float)q1.y - (float)q3.y;
         float w1 = dx * base_a, w2 = dy * base_b;
         float width = w1 + w2;
-        dx = (float)HP(seq[2]).x - (float)HP(seq[0]).x; dy = (float)HP(seq[2]).y - (float)HP(seq[0]).y;
+        dx = (float)q2.x - (float)q0.x; dy = (float)q2.y - (float)q0.y;
         float h1 = -dx * base_b, h2 = dy * base_a;
         float height = h1 + h2;
         float area = width * height;
         if (area <= minarea) { minarea = area; bL = seq[3]; bA = base_a; bW = width; bB = base_b; bH = height; bBt = seq[0]; }
     }
     float A1 = bA, B1 = bB, A2 = -bB, B2 = bA;
-    float lxp = (float)HP(bL).x, lyp = (float)HP(bL).y, bxp = (float)HP(bBt).x, byp = (float)HP(bBt).y;
+    Pt pl = hp(bL), pb = hp(bBt);
+    float lxp = (float)pl.x, lyp = (float)pl.y, bxp = (float)pb.x, byp = (float)pb.y;
     float c1a = A1 * lxp, c1b = lyp * B1; float C1 = c1a + c1b;
     float c2a = A2 * bxp, c2b = byp * B2; float C2 = c2a + c2b;
     float d1 = A1 * B2, d2 = A2 * B1;
@@ -173,7 +150,54 @@ LFD_HD void min_area_rect(const Pt* st, int n, int start, float* vect, float* in
     float w = (float)sqrt(o2d * o2d + o3d * o3d);
     float h = (float)sqrt(o4d * o4d + o5d * o5d);
     normalise_angle(atan2(o3d, o2d) * RAD2DEG, w, h, out);
-#undef HP
+}
+
+// the n == 1 and n == 2 cases of cv2.minAreaRect
+LFD_HD void min_area_rect_small(int n, Pt a, Pt b, Rect* out)
+{
+    const double RAD2DEG = 180.0 / 3.14159265358979323846;
+    out->cx = out->cy = out->w = out->h = out->angle = 0.f;
+    if (n <= 0) return;
+    if (n == 1) { out->cx = (float)a.x; out->cy = (float)a.y; out->angle = -90.f; return; }
+    out->cx = ((float)a.x + (float)b.x) * 0.5f;
+    out->cy = ((float)a.y + (float)b.y) * 0.5f;
+    double dx = (double)((float)b.x - (float)a.x), dy = (double)((float)b.y - (float)a.y);
+    float w = (float)sqrt(dx * dx + dy * dy);
+    normalise_angle(atan2(dy, dx) * RAD2DEG, w, 0.f, out);
+}
+
+// edge vector / inverse length of hull edge p -> q as cv2 computes them
+LFD_HD void hull_edge(Pt p, Pt q, float* vx, float* vy, float* inv)
+{
+    double dx = (double)((float)q.x - (float)p.x), dy = (double)((float)q.y - (float)p.y);
+    *vx = (float)dx; *vy = (float)dy;
+    *inv = (float)(1. / sqrt(dx * dx + dy * dy));
+}
+
+struct RotHull {
+    const Pt* st; int n, start;
+    LFD_HD Pt operator()(int i) const { int j = i + start; if (j >= n) j -= n; return st[j]; }
+};
+
+// cv2.minAreaRect of a strict convex hull st[0..n) taken in the order start, start+1, ... (mod n).
+// vect/inv scratch: 2n and n floats.
+LFD_HD void min_area_rect(const Pt* st, int n, int start, float* vect, float* inv, Rect* out)
+{
+    RotHull hp; hp.st = st; hp.n = n; hp.start = start;
+    if (n <= 2) { min_area_rect_small(n, n > 0 ? hp(0) : Pt{0, 0}, n > 1 ? hp(1) : Pt{0, 0}, out); return; }
+    int left = 0, bottom = 0, right = 0, top = 0;
+    Pt p0 = hp(0);
+    float left_x = (float)p0.x, right_x = left_x, top_y = (float)p0.y, bottom_y = top_y;
+    for (int i = 0; i < n; i++) {
+        Pt p = hp(i), q = hp(i + 1 < n ? i + 1 : 0);
+        float px = (float)p.x, py = (float)p.y;
+        if (px < left_x) { left_x = px; left = i; }
+        if (px > right_x) { right_x = px; right = i; }
+        if (py > top_y) { top_y = py; top = i; }
+        if (py < bottom_y) { bottom_y = py; bottom = i; }
+        hull_edge(p, q, &vect[2 * i], &vect[2 * i + 1], &inv[i]);
+    }
+    min_area_rect_core(hp, n, vect, inv, left, bottom, right, top, out);
 }
 
 // cv2.boxPoints followed by the reference's np.asarray(..., int32) truncation toward zero.

@@ -292,12 +292,17 @@ __device__ __forceinline__ void suf_union(int* p, int a, int b)
     }
 }
 
-#define CCL_BAND_CAP 3584          // runs of one band kept in shared memory (12 B each = 42 KB)
+#define CCL_BAND_CAP 2560          // runs of one band kept in shared memory (12 B each = 30 KB)
+
+// dynamic shared memory of k_ccl_band: CCL_BAND rows of mask words, then the band's parents and runs
+__host__ __device__ inline size_t ccl_band_smem(int WW) { return (size_t)CCL_BAND * WW * 4 + (size_t)CCL_BAND_CAP * 12; }
 
 // 3+4a fused: materialise the runs of a CCL_BAND-row band, link all of its row pairs at once with a
 // union-find that lives in shared memory, and publish band-local roots.  Run ids are raster-ordered, so
 // a band's runs are the contiguous range [rowbase[y0], rowbase[y1]) and local index = id - rowbase[y0].
-// Bands with more runs than CCL_BAND_CAP use the global parent array with the same code path.
+// The band's mask rows are staged in shared memory first (complemented for kind 1), so run ends and
+// neighbour lookups never go back to global memory.  Bands with more runs than CCL_BAND_CAP use the
+// global parent array with the same code path.
 __global__ void __launch_bounds__(256)
 k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
            int pass, Dims d, int kind)
@@ -310,16 +315,27 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     const int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
     const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
     if (nb == 0) return;
-    __shared__ int sp[CCL_BAND_CAP];
-    __shared__ Run srun[CCL_BAND_CAP];
+    extern __shared__ u32 band_sm[];
+    u32* sw = band_sm;                                        // [CCL_BAND][WW]
+    int* sp = (int*)(band_sm + CCL_BAND * d.WW);              // [CCL_BAND_CAP]
+    Run* srun = (Run*)(sp + CCL_BAND_CAP);                    // [CCL_BAND_CAP]
     const bool insm = nb <= CCL_BAND_CAP;
+    const int WW = d.WW;
+    for (int i = threadIdx.x; i < (y1 - y0) * WW; i += blockDim.x) {
+        int yy = i / WW, w = i - yy * WW;
+        u32 v = m[(size_t)(y0 + yy) * WW + w];
+        sw[i] = kind ? (~v & tail_mask(w, d.W)) : v;
+    }
+    __syncthreads();
     // fill: one warp per row, rows strided over the 8 warps
     for (int y = y0 + (threadIdx.x >> 5); y < y1; y += 8) {
         int rb = b.rowbase[y];
-        for (int w = lane_id(); w < d.WW; w += 32) {
-            u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
+        const u32* row = sw + (y - y0) * WW;
+        for (int w = lane_id(); w < WW; w += 32) {
+            u32 cur = row[w], prev = w ? row[w - 1] : 0u;
             u32 starts = cur & ~((cur << 1) | (prev >> 31));
-            int id = rb + b.wpre[(size_t)y * d.WW + w];
+            if (!starts) continue;
+            int id = rb + b.wpre[(size_t)y * WW + w];
             while (starts) {
                 int s = __ffs(starts) - 1;
                 starts &= starts - 1;
@@ -330,8 +346,8 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
                     xe = (w << 5) + s + t - 1;
                 } else {
                     xe = (w << 5) + 31;
-                    for (int w2 = w + 1; w2 < d.WW; w2++) {
-                        u32 nx = ~ccl_word(m, y, w2, d, kind);
+                    for (int w2 = w + 1; w2 < WW; w2++) {
+                        u32 nx = ~row[w2];
                         int t2 = nx ? (__ffs(nx) - 1) : 32;
                         xe = (w2 << 5) + t2 - 1;
                         if (t2 < 32) break;
@@ -350,14 +366,29 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     }
     __syncthreads();
     // link every run with the first run it touches in the row above and in the row below (staircase argument)
+    const int c = kind ? 0 : 1;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
         Run r = insm ? srun[i] : b.runs[base + i];
-        if ((int)r.y > y0) {
-            int j = first_touching(m, b, r.y - 1, r, d, kind);
-            if (j >= 0) { if (insm) suf_union(sp, i, j - base); else uf_union(b.parent, base + i, j); }
-        }
-        if ((int)r.y + 1 < y1) {
-            int j = first_touching(m, b, r.y + 1, r, d, kind);
+        int lo = max((int)r.xs - c, 0), hi = min((int)r.xe + c, d.W - 1);
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy += 2) {
+            int yy = (int)r.y + dy;
+            if (yy < y0 || yy >= y1) continue;
+            const u32* row = sw + (yy - y0) * WW;
+            int j = -1;
+            for (int w = lo >> 5; w <= (hi >> 5); w++) {
+                int blo = max(lo - (w << 5), 0), bhi = min(hi - (w << 5), 31);
+                u32 bits = row[w] & bit_range(blo, bhi);
+                if (bits) {
+                    // run of row yy that contains pixel p
+                    int bit = __ffs(bits) - 1;
+                    u32 cur = row[w], prev = w ? row[w - 1] : 0u;
+                    u32 starts = cur & ~((cur << 1) | (prev >> 31));
+                    u32 upto = (bit == 31) ? 0xffffffffu : ((2u << bit) - 1u);
+                    j = b.rowbase[yy] + b.wpre[(size_t)yy * WW + w] + __popc(starts & upto) - 1;
+                    break;
+                }
+            }
             if (j >= 0) { if (insm) suf_union(sp, i, j - base); else uf_union(b.parent, base + i, j); }
         }
     }

@@ -48,7 +48,10 @@ k_hough_compact(const u32* __restrict__ nzmask, const u32* __restrict__ boxmask,
 
 #define HOUGH_THREADS 256
 
-// grid = (chunks, ngroups, 2*n); dynamic smem = apc * RS * 4 bytes
+// smem accumulator row stride: odd, so that lanes (= angles) voting for similar rho hit different banks
+__host__ __device__ inline int hough_rss(int RS) { return RS | 1; }
+
+// grid = (chunks, ngroups, 2*n); dynamic smem = apc * hough_rss(RS) * 4 bytes
 __global__ void __launch_bounds__(HOUGH_THREADS)
 k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const float* __restrict__ tabSin,
              const float* __restrict__ tabCos, const FrameCtl* __restrict__ ctl, int pass, HoughCfg hc,
@@ -58,15 +61,17 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     int f = blockIdx.z >> 1, which = blockIdx.z & 1;
     if (!ctl[f].active[pass] || !ctl[f].hough[pass]) return;
     int nseg = ctl[f].nseg[which];
+    // lanes = angles; when apc < 32 the warp covers 32/apc segments at once
+    const int per = (hc.apc >= 32) ? 1 : (32 / hc.apc);
+    if (blockIdx.x * (HOUGH_THREADS / 32) * per >= nseg) return;          // no segment for any warp of this CTA
+    const int RSS = hough_rss(hc.RS);
     int g = blockIdx.y;
     int a0 = g * hc.apc;
     int na = min(hc.apc, hc.numangle - a0);
-    for (int i = threadIdx.x; i < hc.apc * hc.RS; i += blockDim.x) acc[i] = 0;
+    for (int i = threadIdx.x; i < hc.apc * RSS; i += blockDim.x) acc[i] = 0;
     __syncthreads();
     const uint2* sg = segs + ((size_t)f * 2 + which) * seg_stride;
     int lane = lane_id();
-    // lanes = angles; when apc < 32 the warp covers 32/apc segments at once
-    int per = (hc.apc >= 32) ? 1 : (32 / hc.apc);
     int sub = lane / hc.apc, a = lane - sub * hc.apc;
     bool live = (per == 1) ? (lane < na) : (sub < per && a < na);
     if (per == 1) { sub = 0; a = lane; }
@@ -75,7 +80,8 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     float c = 0.f, s = 0.f;
     if (live) { c = tabCos[a0 + a]; s = tabSin[a0 + a]; }
     const int off = (hc.numrho - 1) / 2 + 1;
-    int* row = acc + a * hc.RS + off;
+    int* row = acc + a * RSS + off;
+#define HOUGH_R(xx) __float2int_rn(__fadd_rn(__fmul_rn((float)(xx), c), ys))
     for (int si = warp * per; si < nseg; si += nwarps * per) {
         int idx = si + sub;
         if (!live || idx >= nseg) continue;
@@ -84,29 +90,52 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
         u32 m = sgv.y;
         float ys = __fmul_rn((float)y, s);
         int fb = __ffs(m) - 1, lb = 31 - __clz(m);
-        int r1 = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + fb), c), ys));
-        int r2 = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + lb), c), ys));
+        int r1 = HOUGH_R(x0 + fb);
+        int r2 = HOUGH_R(x0 + lb);
         if (r1 == r2) {
             atomicAdd(&row[r1], __popc(m));
+        } else if (abs(r2 - r1) <= 2 && __popc(m) > 4) {
+            // r is monotone in x: locate the (at most two) bin boundaries inside the word by bisection
+            int lo = fb, hi = lb;                       // R(lo) == r1, R(hi) != r1
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (HOUGH_R(x0 + mid) == r1) lo = mid; else hi = mid;
+            }
+            int c1 = __popc(m & bit_range(fb, lo));
+            atomicAdd(&row[r1], c1);
+            int rm = HOUGH_R(x0 + hi);
+            if (rm == r2) {
+                atomicAdd(&row[r2], __popc(m & bit_range(hi, lb)));
+            } else {
+                int lo2 = hi, hi2 = lb;                 // R(lo2) == rm, R(hi2) == r2
+                while (hi2 - lo2 > 1) {
+                    int mid = (lo2 + hi2) >> 1;
+                    if (HOUGH_R(x0 + mid) == rm) lo2 = mid; else hi2 = mid;
+                }
+                int c2 = __popc(m & bit_range(hi, lo2));
+                if (c2) atomicAdd(&row[rm], c2);
+                atomicAdd(&row[r2], __popc(m & bit_range(hi2, lb)));
+            }
         } else {
             int cur = r1, cnt = 1;
             m &= m - 1;
             while (m) {
                 int b = __ffs(m) - 1;
                 m &= m - 1;
-                int r = __float2int_rn(__fadd_rn(__fmul_rn((float)(x0 + b), c), ys));
+                int r = HOUGH_R(x0 + b);
                 if (r == cur) cnt++;
                 else { atomicAdd(&row[cur], cnt); cur = r; cnt = 1; }
             }
             atomicAdd(&row[cur], cnt);
         }
     }
+#undef HOUGH_R
     __syncthreads();
     int* gacc = accum + ((size_t)f * 2 + which) * accum_stride;
-    for (int i = threadIdx.x; i < na * hc.RS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < na * RSS; i += blockDim.x) {
         int v = acc[i];
         if (v) {
-            int aa = i / hc.RS, col = i - aa * hc.RS;
+            int aa = i / RSS, col = i - aa * RSS;
             atomicAdd(&gacc[(size_t)(a0 + aa + 1) * hc.RS + col], v);
         }
     }

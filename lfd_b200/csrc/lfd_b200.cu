@@ -104,6 +104,11 @@ struct lfd_handle {
     float timings[N_TIMINGS];
     cudaEvent_t mark[4];              // caller-placed timestamps on the handle's stream (lfd_timer_mark)
     bool mark_valid[4];
+    // developer aid (env LFD_KTIMING=1): one event after every launch, reported by source line
+    bool ktiming = false;
+    std::vector<cudaEvent_t> kev;
+    std::vector<int> kline;
+    int kn = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -118,12 +123,21 @@ struct lfd_handle {
 #define LAUNCH_CHECK()                                                                             \
     do {                                                                                           \
         h->launches++;                                                                             \
+        if (h->ktiming) ktime_mark(h, __LINE__);                                                   \
         cudaError_t e_ = cudaGetLastError();                                                       \
         if (e_ != cudaSuccess) {                                                                   \
             h->err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " at line " + std::to_string(__LINE__); \
             return LFD_E_CUDA;                                                                     \
         }                                                                                          \
     } while (0)
+
+static void ktime_mark(lfd_handle* h, int line)
+{
+    if (h->kn >= (int)h->kev.size()) { cudaEvent_t e; cudaEventCreate(&e); h->kev.push_back(e); h->kline.push_back(0); }
+    h->kline[h->kn] = line;
+    cudaEventRecord(h->kev[h->kn], h->stream);
+    h->kn++;
+}
 
 template <typename T>
 static int dev_alloc(lfd_handle* h, T** p, size_t count)
@@ -229,14 +243,14 @@ static int hough_setup(lfd_handle* h, HoughBufs* hb, int H, int W, double rho_, 
     hc.theta = (float)theta_;
     hc.threshold = threshold;
     const size_t smem_budget = 96 * 1024;
-    int apc = (int)(smem_budget / ((size_t)hc.RS * 4));
+    int apc = (int)(smem_budget / ((size_t)hough_rss(hc.RS) * 4));
     if (apc > 32) apc = 32;
     if (apc < 1) { h->err = "HoughLines: rho too fine for the shared-memory accumulator (numrho too large)"; return LFD_E_UNSUPPORTED; }
     if (apc < 32) { int p = 1; while (p * 2 <= apc) p *= 2; apc = p; }   // power of two so sub-warps tile a warp
     if (apc > hc.numangle) apc = hc.numangle < 32 ? next_pow2(hc.numangle) : 32;
     hc.apc = apc;
     hc.ngroups = (hc.numangle + apc - 1) / apc;
-    hb->smem = (size_t)apc * hc.RS * 4;
+    hb->smem = (size_t)apc * hough_rss(hc.RS) * 4;
     hb->hc = hc;
     // tables, exactly as OpenCV builds them (float accumulation of the angle)
     std::vector<float> ts(hc.numangle), tc(hc.numangle);
@@ -313,6 +327,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     if (device < 0 || device >= ndev) { h->err = "no such CUDA device"; return LFD_E_CUDA; }
     CK(cudaSetDevice(device));
     h->device = device;
+    { const char* kt = getenv("LFD_KTIMING"); h->ktiming = kt && kt[0] == '1'; }
     if (max_batch < 1 || H < 8 || W < 8) { h->err = "bad batch or frame size"; return LFD_E_ARG; }
     if (W % 4 != 0) { h->err = "frame width must be a multiple of 4"; return LFD_E_UNSUPPORTED; }
     if (W > 4096 || H > 65535) { h->err = "frame too large (W <= 4096, H <= 65535)"; return LFD_E_UNSUPPORTED; }
@@ -327,6 +342,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     long long worst = (long long)H * ((W + 1) / 2);
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
     for (int i = 0; i < 4; i++) { CK(cudaEventCreate(&h->mark[i])); h->mark_valid[i] = true; }
 
@@ -547,7 +563,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[0], h->ctl, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
     k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->edges[pass], h->ctl, pass, d); LAUNCH_CHECK();
@@ -557,21 +573,21 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     // background runs: hole contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[1], h->ctl, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 4], s));
     // rectangles + box image
-    k_rects<<<dim3(32, n), 128, 0, s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, d, pp.minAreaRectMinLen, pp.lwTresh); LAUNCH_CHECK();
+    k_rects_warp<<<dim3(64, n), RECT_WARPS * 32, 0, s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, d, pp.minAreaRectMinLen, pp.lwTresh); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], h->ctl, pass, d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 5], s));
     // Hough on the morphology output and on the box image
     CK(cudaMemsetAsync(hb.accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
     k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs, h->ctl, pass, d, (size_t)d.NW); LAUNCH_CHECK();
-    k_hough_vote<<<dim3(8, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs, hb.accum, hb.tabSin, hb.tabCos, h->ctl, pass,
+    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs, hb.accum, hb.tabSin, hb.tabCos, h->ctl, pass,
                                                                             hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
     int cells = hb.hc.numangle * hb.hc.numrho;
     int pblocks = (cells + 255) / 256; if (pblocks > 64) pblocks = 64;
@@ -596,6 +612,7 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     if (!h->have_params) { h->err = "lfd_set_params has not been called"; return LFD_E_STATE; }
     CK(cudaMemsetAsync(h->counters_d, 0, 16 * sizeof(int64_t), s));
     CK(cudaEventRecord(h->ev[0], s));
+    if (h->ktiming) { h->kn = 0; ktime_mark(h, 0); }
     k_ctl_init<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->res_d, n, mode != 2, mode != 1); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->hist, 0, (size_t)2 * h->B * 256 * sizeof(u32), s));
     if (mode == 0) {
@@ -937,6 +954,20 @@ extern "C" int lfd_timer_elapsed(lfd_handle* h, int slot_start, lfd_handle* h_en
     CK(cudaEventSynchronize(h->mark[slot_start]));
     CK(cudaEventSynchronize(h_end->mark[slot_end]));
     CK(cudaEventElapsedTime(ms, h->mark[slot_start], h_end->mark[slot_end]));
+    return LFD_OK;
+}
+
+// developer aid: per-launch device times of the last run when LFD_KTIMING=1 (source line of the launch, ms)
+extern "C" int lfd_get_ktimings(lfd_handle* h, int* lines, float* ms, int max_entries, int* n_entries)
+{
+    if (!h || !lines || !ms || !n_entries) return LFD_E_ARG;
+    int n = 0;
+    for (int i = 1; i < h->kn && n < max_entries; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->kev[i - 1], h->kev[i]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
+        lines[n] = h->kline[i]; ms[n] = t; n++;
+    }
+    *n_entries = n;
     return LFD_OK;
 }
 
