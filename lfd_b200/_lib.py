@@ -315,7 +315,7 @@ class Handle:
         c = (ctypes.c_int64 * 16)()
         self._ck(self._L.lfd_get_counters(self.h, c, 16))
         names = ["nnz_equ", "nnz_box", "votes", "runs_fg", "runs_bg", "contours", "passing_rects", "frames_dim",
-                 "frames_hough", "frames_bright_run", "frames_dim_run"]
+                 "frames_hough", "frames_bright_run", "frames_dim_run", "rects_warp_path", "rects_thread_overflow"]
         return {k: int(c[i]) for i, k in enumerate(names)}
 
     def timer_mark(self, slot):

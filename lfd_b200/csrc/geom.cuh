@@ -83,16 +83,51 @@ LFD_HD void normalise_angle(double ang, float w, float h, Rect* r)
 // Rotating calipers of cv2.minAreaRect (4.13) on a strict convex hull of n >= 3 vertices.  `hp(i)` returns
 // vertex i (0 <= i < n) in caliper order; vect[2i..2i+1] = edge i -> i+1 as floats, inv[i] = 1/|edge i|;
 // left/bottom/right/top = FIRST index of min x / min y / max x / max y (cv2 scans with strict compares).
+// edge vector / inverse length of hull edge p -> q as cv2 computes them
+LFD_HD void hull_edge(Pt p, Pt q, float* vx, float* vy, float* inv)
+{
+    double dx = (double)((float)q.x - (float)p.x), dy = (double)((float)q.y - (float)p.y);
+    *vx = (float)dx; *vy = (float)dy;
+    *inv = (float)(1. / sqrt(dx * dx + dy * dy));
+}
+
+// edge provider backed by precomputed arrays
+struct ArrEdges {
+    const float* vect; const float* inv;
+    LFD_HD void vec(int i, float* vx, float* vy) const { *vx = vect[2 * i]; *vy = vect[2 * i + 1]; }
+    LFD_HD float invlen(int i) const { return inv[i]; }
+};
+
+// edge provider that recomputes edge i from the hull vertices (same float results, no scratch arrays)
 template <class HP>
-LFD_HD void min_area_rect_core(const HP& hp, int n, const float* vect, const float* inv, int left, int bottom,
+struct FlyEdges {
+    HP hp; int n;
+    LFD_HD void vec(int i, float* vx, float* vy) const
+    {
+        Pt p = hp(i), q = hp(i + 1 < n ? i + 1 : 0);
+        *vx = (float)q.x - (float)p.x; *vy = (float)q.y - (float)p.y;
+    }
+    LFD_HD float invlen(int i) const
+    {
+        float vx, vy, iv;
+        hull_edge(hp(i), hp(i + 1 < n ? i + 1 : 0), &vx, &vy, &iv);
+        return iv;
+    }
+};
+
+template <class HP, class EV>
+LFD_HD void min_area_rect_core(const HP& hp, int n, const EV& ev, int left, int bottom,
                                int right, int top, Rect* out)
 {
     const double RAD2DEG = 180.0 / 3.14159265358979323846;
     float orientation = 0.f;
     {
-        double ax = vect[2 * (n - 1)], ay = vect[2 * (n - 1) + 1];
+        float fx, fy;
+        ev.vec(n - 1, &fx, &fy);
+        double ax = fx, ay = fy;
         for (int i = 0; i < n; i++) {
-            double bx = vect[2 * i], by = vect[2 * i + 1];
+            ev.vec(i, &fx, &fy);
+            double bx = fx, by = fy;
             double c = ax * by - ay * bx;
             if (c != 0) { orientation = c > 0 ? 1.f : -1.f; break; }
             ax = bx; ay = by;
@@ -104,11 +139,15 @@ LFD_HD void min_area_rect_core(const HP& hp, int n, const float* vect, const flo
     int bL = 0, bBt = 0;
     for (int k = 0; k < n; k++) {
         // edge with the smallest rotation: exact cross products of the rotated edge vectors
-        float rvx[4], rvy[4];
-        rvx[0] = vect[2 * seq[0]];      rvy[0] = vect[2 * seq[0] + 1];
-        rvx[1] = vect[2 * seq[1] + 1];  rvy[1] = -vect[2 * seq[1]];
-        rvx[2] = -vect[2 * seq[2]];     rvy[2] = -vect[2 * seq[2] + 1];
-        rvx[3] = -vect[2 * seq[3] + 1]; rvy[3] = vect[2 * seq[3]];
+        float rvx[4], rvy[4], ex[4], ey[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int i = 0; i < 4; i++) ev.vec(seq[i], &ex[i], &ey[i]);
+        rvx[0] = ex[0];  rvy[0] = ey[0];
+        rvx[1] = ey[1];  rvy[1] = -ex[1];
+        rvx[2] = -ex[2]; rvy[2] = -ey[2];
+        rvx[3] = -ey[3]; rvy[3] = ex[3];
         int me = 0;
         for (int i = 1; i < 4; i++) {
             float tx = rvy[i], ty = -rvx[i];
@@ -116,7 +155,8 @@ LFD_HD void min_area_rect_core(const HP& hp, int n, const float* vect, const flo
             if (t1 + t2 < 0) me = i;
         }
         int pi = seq[me];
-        float lx = vect[2 * pi] * inv[pi], ly = vect[2 * pi + 1] * inv[pi];
+        float il = ev.invlen(pi);
+        float lx = ex[me] * il, ly = ey[me] * il;
         switch (me) {
         case 0: base_a = lx; base_b = ly; break;
         case 1: base_a = ly; base_b = -lx; break;
@@ -166,14 +206,6 @@ LFD_HD void min_area_rect_small(int n, Pt a, Pt b, Rect* out)
     normalise_angle(atan2(dy, dx) * RAD2DEG, w, 0.f, out);
 }
 
-// edge vector / inverse length of hull edge p -> q as cv2 computes them
-LFD_HD void hull_edge(Pt p, Pt q, float* vx, float* vy, float* inv)
-{
-    double dx = (double)((float)q.x - (float)p.x), dy = (double)((float)q.y - (float)p.y);
-    *vx = (float)dx; *vy = (float)dy;
-    *inv = (float)(1. / sqrt(dx * dx + dy * dy));
-}
-
 struct RotHull {
     const Pt* st; int n, start;
     LFD_HD Pt operator()(int i) const { int j = i + start; if (j >= n) j -= n; return st[j]; }
@@ -197,7 +229,8 @@ LFD_HD void min_area_rect(const Pt* st, int n, int start, float* vect, float* in
         if (py < bottom_y) { bottom_y = py; bottom = i; }
         hull_edge(p, q, &vect[2 * i], &vect[2 * i + 1], &inv[i]);
     }
-    min_area_rect_core(hp, n, vect, inv, left, bottom, right, top, out);
+    ArrEdges ev; ev.vect = vect; ev.inv = inv;
+    min_area_rect_core(hp, n, ev, left, bottom, right, top, out);
 }
 
 // cv2.boxPoints followed by the reference's np.asarray(..., int32) truncation toward zero.

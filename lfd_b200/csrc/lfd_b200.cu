@@ -343,6 +343,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
+    CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_smem(max_batch)));
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
     for (int i = 0; i < 4; i++) { CK(cudaEventCreate(&h->mark[i])); h->mark_valid[i] = true; }
 
@@ -580,7 +581,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 4], s));
     // rectangles + box image
-    k_rects_warp<<<dim3(64, n), RECT_WARPS * 32, 0, s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, d, pp.minAreaRectMinLen, pp.lwTresh); LAUNCH_CHECK();
+    k_rects_warp<<<148 * 4, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], h->ctl, pass, d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 5], s));

@@ -32,6 +32,7 @@ for _ in range(R):
         seen[line] += 1
         key = (line, seen[line])
         acc[key] = acc.get(key, 0.0) + ms
+print("counters", h.counters())
 tot = sum(acc.values()) / R
 print("total %.3f ms / step of %d frames" % (tot, B))
 for (line, k), ms in acc.items():
