@@ -116,3 +116,167 @@ k_canny_nms(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
         }
     }
 }
+
+// ================================================================================================
+// Register-marching variant (production path when W % 8 == 0), same strip geometry as k_morph_march:
+// a warp owns 64 4-pixel words (lanes 2..29 produce output: 224 px = 7 mask words) and marches down
+// NMS_R rows.  Sobel runs on u16x2 pairs (VIADD.16x2 / VIMNMX.S16x2): per arriving image row the
+// horizontal [1,2,1] sum and the horizontal difference are formed once and kept in 3-row register
+// rings, dx/dy/magnitude are their vertical combinations; the direction test of OpenCV (32-bit
+// integer tan 22.5) is scalar per pixel and only runs on rows where some pixel has a gradient.
+// Empty strip chunks (no non-zero input pixel, from the morphology kernel's 1-bit mask) are skipped.
+// ================================================================================================
+#include "k_morph.cuh"
+
+#define NMS_R 64
+
+__device__ __forceinline__ u32 vneg2(u32 a) { return __vadd2(~a, 0x00010001u); }
+__device__ __forceinline__ u32 vsub2(u32 a, u32 b) { return __vadd2(a, vneg2(b)); }
+__device__ __forceinline__ u32 vabs2s(u32 a) { return __vmaxs2(a, vneg2(a)); }
+
+template <bool TAP>
+__global__ void __launch_bounds__(128)
+k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restrict__ cand, u32* __restrict__ strong,
+            u8* __restrict__ nms_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int nstrips, int nunits,
+            int low, int high)
+{
+    const int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= nunits) return;
+    // per warp: 3-row rings of magnitude / dx / dy as 16-bit planes of the 256-px strip.  The SIMD stage
+    // writes them in "8 px per lane" layout, the decision stage reads them in "1 px per lane" layout, so
+    // a 10-px run of gradient pixels occupies 10 lanes for one iteration instead of 2 lanes for 8.
+    __shared__ __align__(16) u16 sM[4][3][256];
+    __shared__ __align__(16) short sDX[4][3][256];
+    __shared__ __align__(16) short sDY[4][3][256];
+    const int wid = threadIdx.x >> 5;
+    const int chunk = unit / nstrips, s = unit - chunk * nstrips;
+    const int lane = lane_id();
+    const int Ww = d.W >> 2;
+    const int wx = s * MARCH_UW - MARCH_HW + 2 * lane;
+    const bool col_in = wx >= 0 && wx < Ww;
+    const int y0 = chunk * NMS_R, y1 = min(y0 + NMS_R, d.H);
+    const int mw0 = s * (MARCH_UW / 8);                     // first mask word of the strip
+    u32* candf = cand + (size_t)f * d.NW;
+    u32* strongf = strong + (size_t)f * d.NW;
+    const int nwords = min(MARCH_UW / 8, d.WW - mw0);        // mask words this strip owns (<= 7)
+
+    // any non-zero input pixel in the window of this unit?  mask words 7s-1 .. 7s+7, rows y0-2 .. y1+1
+    {
+        const int ra = max(y0 - 2, 0), rb = min(y1 + 1, d.H - 1);
+        const int wa = max(mw0 - 1, 0), wb = min(mw0 + 7, d.WW - 1);
+        const int nw = wb - wa + 1, tot = (rb - ra + 1) * nw;
+        u32 any = 0;
+        for (int i = lane; i < tot; i += 32) {
+            int yy = ra + i / nw, w = wa + i % nw;
+            any |= nz[(size_t)f * d.NW + (size_t)yy * d.WW + w];
+        }
+        if (!__any_sync(FULLMASK, any != 0)) {
+            for (int y = y0; y < y1; y++) {
+                if (lane < nwords) { candf[(size_t)y * d.WW + mw0 + lane] = 0u; strongf[(size_t)y * d.WW + mw0 + lane] = 0u; }
+                if (TAP)
+                    for (int x = lane; x < 32 * nwords; x += 32)
+                        if (32 * mw0 + x < d.W) nms_tap[(size_t)f * d.N + (size_t)y * d.W + 32 * mw0 + x] = 0;
+            }
+            return;
+        }
+    }
+
+    const uint2* g = reinterpret_cast<const uint2*>(img + (size_t)f * d.N);
+    const u32* gw = reinterpret_cast<const u32*>(img + (size_t)f * d.N);
+    u32 HD[3][4], H3[3][4];
+    bool nzf[3] = {false, false, false};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) { HD[k][c] = 0; H3[k][c] = 0; }
+    for (int i = lane; i < 3 * 256 / 2; i += 32) reinterpret_cast<u32*>(&sM[wid][0][0])[i] = 0u;
+    __syncwarp();
+    const int TG22 = 13573;
+    for (int yb = y0 - 2; yb <= y1 + 1; yb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int yi = yb + u;
+            const int yl = min(max(yi, 0), d.H - 1);                 // BORDER_REPLICATE rows
+            uint2 v;
+            if (col_in) v = __ldg(g + (((size_t)yl * Ww + wx) >> 1));
+            else {                                                   // BORDER_REPLICATE columns
+                u32 e = (wx < 0) ? (__ldg(gw + (size_t)yl * Ww) & 0xffu) : (__ldg(gw + (size_t)yl * Ww + Ww - 1) >> 24);
+                v.x = v.y = e * 0x01010101u;
+            }
+            u32 p[4];
+            p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
+            p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
+            const u32 eL = __shfl_up_sync(FULLMASK, p[3], 1), eR = __shfl_down_sync(FULLMASK, p[0], 1);
+            u32 S[5];                                                // S[j] = (px 2j-1, px 2j) of the lane's 8 pixels
+            S[0] = __byte_perm(eL, p[0], 0x5432);
+            S[1] = __byte_perm(p[0], p[1], 0x5432);
+            S[2] = __byte_perm(p[1], p[2], 0x5432);
+            S[3] = __byte_perm(p[2], p[3], 0x5432);
+            S[4] = __byte_perm(p[3], eR, 0x5432);
+            const int sa = (u + 1) % 3, sb = (u + 2) % 3, sc = u % 3;   // ring slots of rows yi-2, yi-1, yi
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                HD[sc][c] = vsub2(S[c + 1], S[c]);                                  // p(x+1) - p(x-1)
+                H3[sc][c] = __vadd2(__vadd2(S[c], S[c + 1]), __vadd2(p[c], p[c]));  // p(x-1) + 2p(x) + p(x+1)
+            }
+            // gradient of the centre row yc = yi - 1 -> shared-memory slot sb
+            const int yc = yi - 1;
+            const bool cin = yc >= 0 && yc < d.H && col_in;
+            u32 mg[4], dxv[4], dyv[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                dxv[c] = __vadd2(__vadd2(HD[sa][c], HD[sc][c]), __vadd2(HD[sb][c], HD[sb][c]));
+                dyv[c] = vsub2(H3[sc][c], H3[sa][c]);
+                mg[c] = cin ? __vadd2(vabs2s(dxv[c]), vabs2s(dyv[c])) : 0u;
+            }
+            nzf[sb] = (mg[0] | mg[1] | mg[2] | mg[3]) != 0u;
+            reinterpret_cast<uint4*>(&sM[wid][sb][0])[lane] = make_uint4(mg[0], mg[1], mg[2], mg[3]);
+            if (nzf[sb]) {
+                reinterpret_cast<uint4*>(&sDX[wid][sb][0])[lane] = make_uint4(dxv[0], dxv[1], dxv[2], dxv[3]);
+                reinterpret_cast<uint4*>(&sDY[wid][sb][0])[lane] = make_uint4(dyv[0], dyv[1], dyv[2], dyv[3]);
+            }
+            __syncwarp();
+            // non-maximum suppression of row yn = yi - 2 (rows yn-1, yn, yn+1 in slots sc, sa, sb)
+            const int yn = yi - 2;
+            if (yn >= y0 && yn < y1) {                               // warp-uniform
+                const u32 bal = __ballot_sync(FULLMASK, nzf[sa]);
+                u32 myc = 0, mys = 0;                                // lane g keeps mask word g
+                const u16* Mu = sM[wid][sc]; const u16* Mc = sM[wid][sa]; const u16* Md = sM[wid][sb];
+#pragma unroll
+                for (int gi = 0; gi < 7; gi++) {
+                    int cls = 0;
+                    if ((bal >> (2 + 4 * gi)) & 0xfu) {              // some pixel of this 32-px group has a gradient
+                        const int x = 16 + 32 * gi + lane;           // pixel index inside the 256-px strip
+                        const int mm = Mc[x];
+                        if (mm > low) {
+                            const int dx = sDX[wid][sa][x], dy = sDY[wid][sa][x];
+                            const int ax = abs(dx), ay = abs(dy) << 15;
+                            const int tg22x = ax * TG22;
+                            bool keep;
+                            if (ay < tg22x) keep = mm > Mc[x - 1] && mm >= Mc[x + 1];
+                            else {
+                                const int tg67x = tg22x + (ax << 16);
+                                if (ay > tg67x) keep = mm > Mu[x] && mm >= Md[x];
+                                else {
+                                    const int sg = ((dx ^ dy) < 0) ? -1 : 1;
+                                    keep = mm > Mu[x - sg] && mm > Md[x + sg];
+                                }
+                            }
+                            if (keep) cls = mm > high ? 2 : 1;
+                        }
+                        const u32 bc = __ballot_sync(FULLMASK, cls != 0), bs = __ballot_sync(FULLMASK, cls == 2);
+                        if (lane == gi) { myc = bc; mys = bs; }
+                    }
+                    if (TAP) {
+                        const int xg = 32 * (mw0 + gi) + lane;
+                        if (gi < nwords && xg < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + xg] = (u8)cls;
+                    }
+                }
+                if (lane < nwords) { candf[(size_t)yn * d.WW + mw0 + lane] = myc; strongf[(size_t)yn * d.WW + mw0 + lane] = mys; }
+            }
+            __syncwarp();
+        }
+    }
+}

@@ -558,8 +558,17 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
         if (!h->nms_tap[pass]) { int rc = dev_alloc(h, &h->nms_tap[pass], (size_t)h->B * d.N); if (rc) return rc; }
         ntap = h->nms_tap[pass];
     }
-    dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
-    k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255); LAUNCH_CHECK();
+    if ((d.W % 8) == 0) {
+        const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
+        const int nunits = nstrips * nchunks;
+        dim3 gg((nunits + 3) / 4, n);
+        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, nstrips, nunits, 0, 255);
+        else k_nms_march<false><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, nstrips, nunits, 0, 255);
+    } else {
+        dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
+        k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255);
+    }
+    LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 2], s));
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
