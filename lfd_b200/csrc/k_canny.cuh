@@ -186,7 +186,9 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
     const uint2* g = reinterpret_cast<const uint2*>(img + (size_t)f * d.N);
     const u32* gw = reinterpret_cast<const u32*>(img + (size_t)f * d.N);
     u32 HD[3][4], H3[3][4];
-    bool nzf[3] = {false, false, false};
+    bool nzf[3] = {false, false, false};          // this lane has a gradient pixel in the row of slot k
+    bool nzf_any[3] = {false, false, false};      // ... some lane of the warp has (the smem row of slot k is not all-zero)
+    bool rz[3] = {false, false, false};           // input row of slot k is all-zero across the strip
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -194,16 +196,51 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
     for (int i = lane; i < 3 * 256 / 2; i += 32) reinterpret_cast<u32*>(&sM[wid][0][0])[i] = 0u;
     __syncwarp();
     const int TG22 = 13573;
+    // rows are requested NMS_PF steps ahead of their use (software pipeline; the kernel is latency-bound)
+    auto load_row = [&](int yi) -> uint2 {
+        const int yl = min(max(yi, 0), d.H - 1);                     // BORDER_REPLICATE rows
+        uint2 v;
+        if (col_in) v = __ldg(g + (((size_t)yl * Ww + wx) >> 1));
+        else {                                                       // BORDER_REPLICATE columns
+            u32 e = (wx < 0) ? (__ldg(gw + (size_t)yl * Ww) & 0xffu) : (__ldg(gw + (size_t)yl * Ww + Ww - 1) >> 24);
+            v.x = v.y = e * 0x01010101u;
+        }
+        return v;
+    };
+    uint2 nxt[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) nxt[u] = load_row(y0 - 2 + u);
     for (int yb = y0 - 2; yb <= y1 + 1; yb += 3) {
+        uint2 cur[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) cur[u] = nxt[u];
+        if (yb + 3 <= y1 + 1) {
+#pragma unroll
+            for (int u = 0; u < 3; u++) nxt[u] = load_row(yb + 3 + u);
+        }
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const int yi = yb + u;
-            const int yl = min(max(yi, 0), d.H - 1);                 // BORDER_REPLICATE rows
-            uint2 v;
-            if (col_in) v = __ldg(g + (((size_t)yl * Ww + wx) >> 1));
-            else {                                                   // BORDER_REPLICATE columns
-                u32 e = (wx < 0) ? (__ldg(gw + (size_t)yl * Ww) & 0xffu) : (__ldg(gw + (size_t)yl * Ww + Ww - 1) >> 24);
-                v.x = v.y = e * 0x01010101u;
+            const uint2 v = cur[u];
+            const int sa = (u + 1) % 3, sb = (u + 2) % 3, sc = u % 3;   // ring slots of rows yi-2, yi-1, yi
+            rz[sc] = !__any_sync(FULLMASK, (v.x | v.y) != 0u);
+            if (rz[0] && rz[1] && rz[2]) {
+                // three all-zero input rows across the strip: zero gradient on the centre row, nothing to suppress
+#pragma unroll
+                for (int c = 0; c < 4; c++) { HD[sc][c] = 0; H3[sc][c] = 0; }
+                if (nzf_any[sb]) reinterpret_cast<uint4*>(&sM[wid][sb][0])[lane] = make_uint4(0u, 0u, 0u, 0u);
+                nzf[sb] = false; nzf_any[sb] = false;
+                const int yn = yi - 2;
+                __syncwarp();
+                if (yn >= y0 && yn < y1) {
+                    if (!nzf_any[sa]) {
+                        if (lane < nwords) { candf[(size_t)yn * d.WW + mw0 + lane] = 0u; strongf[(size_t)yn * d.WW + mw0 + lane] = 0u; }
+                        if (TAP)
+                            for (int x = lane; x < 32 * nwords; x += 32)
+                                if (32 * mw0 + x < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + 32 * mw0 + x] = 0;
+                        continue;
+                    }
+                } else continue;
             }
             u32 p[4];
             p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
@@ -215,7 +252,6 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
             S[2] = __byte_perm(p[1], p[2], 0x5432);
             S[3] = __byte_perm(p[2], p[3], 0x5432);
             S[4] = __byte_perm(p[3], eR, 0x5432);
-            const int sa = (u + 1) % 3, sb = (u + 2) % 3, sc = u % 3;   // ring slots of rows yi-2, yi-1, yi
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 HD[sc][c] = vsub2(S[c + 1], S[c]);                                  // p(x+1) - p(x-1)
@@ -232,6 +268,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                 mg[c] = cin ? __vadd2(vabs2s(dxv[c]), vabs2s(dyv[c])) : 0u;
             }
             nzf[sb] = (mg[0] | mg[1] | mg[2] | mg[3]) != 0u;
+            nzf_any[sb] = __any_sync(FULLMASK, nzf[sb]);
             reinterpret_cast<uint4*>(&sM[wid][sb][0])[lane] = make_uint4(mg[0], mg[1], mg[2], mg[3]);
             if (nzf[sb]) {
                 reinterpret_cast<uint4*>(&sDX[wid][sb][0])[lane] = make_uint4(dxv[0], dxv[1], dxv[2], dxv[3]);

@@ -291,13 +291,32 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 #pragma unroll
         for (int c = 0; c < 4; c++) dR[k][c] = 0;
 
+    // software pipeline: the U rows of the next block are requested before the current block is processed,
+    // so the dependent min/max chain never waits on a global load (the kernel is latency-, not bandwidth-bound)
+    uint2 nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int y = yfirst + u;
+        nxt[u] = make_uint2(0u, 0u);
+        if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + (((size_t)y * Ww + wx) >> 1));
+    }
     for (int yb = yfirst; yb <= ylast; yb += U) {
+        uint2 cur[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) cur[u] = nxt[u];
+        if (yb + U <= ylast) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int y = yb + U + u;
+                nxt[u] = make_uint2(0u, 0u);
+                if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + (((size_t)y * Ww + wx) >> 1));
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int y = yb + u;
-            uint2 v = HAS_E ? make_uint2(0xffffffffu, 0xffffffffu) : make_uint2(0u, 0u);
+            const uint2 v = cur[u];
             const bool rin = y >= 0 && y < d.H;
-            if (rin && col_in) v = __ldg(g + (((size_t)y * Ww + wx) >> 1));
             u32 p[4];
             if (HAS_E && !(rin && col_in)) {
                 p[0] = p[1] = p[2] = p[3] = 0xffffffffu;
