@@ -331,6 +331,15 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     for (int y = y0 + (threadIdx.x >> 5); y < y1; y += 8) {
         int rb = b.rowbase[y];
         const u32* row = sw + (y - y0) * WW;
+        // words that are not all-ones, one ballot per 32-word chunk (W <= 4096 -> at most 4 chunks): a run
+        // that leaves its word ends in the next such word, found with a bit scan instead of a serial walk
+        // (the background of a sparse frame is one frame-wide run per row)
+        u32 nf[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int w = c * 32 + lane_id();
+            nf[c] = __ballot_sync(FULLMASK, w >= WW || row[w] != 0xffffffffu);
+        }
         for (int w = lane_id(); w < WW; w += 32) {
             u32 cur = row[w], prev = w ? row[w - 1] : 0u;
             u32 starts = cur & ~((cur << 1) | (prev >> 31));
@@ -345,13 +354,17 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
                 if (s + t < 32) {
                     xe = (w << 5) + s + t - 1;
                 } else {
-                    xe = (w << 5) + 31;
-                    for (int w2 = w + 1; w2 < WW; w2++) {
-                        u32 nx = ~row[w2];
-                        int t2 = nx ? (__ffs(nx) - 1) : 32;
-                        xe = (w2 << 5) + t2 - 1;
-                        if (t2 < 32) break;
+                    int w2 = WW;                                   // first not-full word after w
+                    const int c0 = w >> 5, pos = w & 31;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if (c < c0 || w2 < WW) continue;
+                        u32 mbits = nf[c];
+                        if (c == c0) mbits &= (pos == 31) ? 0u : (0xffffffffu << (pos + 1));
+                        if (mbits) w2 = c * 32 + __ffs(mbits) - 1;
                     }
+                    if (w2 >= WW) xe = (WW << 5) - 1;
+                    else xe = (w2 << 5) + __ffs(~row[w2]) - 2;
                 }
                 Run r; r.xs = (u16)((w << 5) + s); r.xe = (u16)xe; r.y = (u16)y; r.pad = 0;
                 b.runs[id] = r;

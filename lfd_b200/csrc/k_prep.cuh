@@ -10,23 +10,26 @@
 #pragma once
 #include "common.cuh"
 
-// rects: (r0, r1, c0, c1) half-open on the UN-flipped image, per frame via rect_off.
+// rects: (r0, r1, c0, c1) half-open on the UN-flipped image; rect_off[n+1] indexes them per frame.
 // mask: [n][H][WW] bit per pixel in the FLIPPED orientation (row H-1-r).
-__global__ void k_star_mask(const int4* __restrict__ rects, const int* __restrict__ rect_off,
-                            u32* __restrict__ mask, Dims d)
+// One warp per rectangle over the flat list of ALL frames (the frame is found by bisection of rect_off),
+// so the grid is proportional to the number of stars, not to frames x the densest frame.
+__global__ void __launch_bounds__(128)
+k_star_mask(const int4* __restrict__ rects, const int* __restrict__ rect_off, int nframes, int total,
+            u32* __restrict__ mask, Dims d)
 {
-    int f = blockIdx.y;
-    int nr = rect_off[f + 1] - rect_off[f];
-    int ri = blockIdx.x;
-    if (ri >= nr) return;
-    int4 r = rects[rect_off[f] + ri];
+    const int ri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ri >= total) return;
+    int flo = 0, fhi = nframes;                     // largest f with rect_off[f] <= ri
+    while (fhi - flo > 1) { int mid = (flo + fhi) >> 1; if (rect_off[mid] <= ri) flo = mid; else fhi = mid; }
+    const int4 r = rects[ri];
     int r0 = max(r.x, 0), r1 = min(r.y, d.H), c0 = max(r.z, 0), c1 = min(r.w, d.W);
     if (r0 >= r1 || c0 >= c1) return;
     int w0 = c0 >> 5, w1 = (c1 - 1) >> 5;
     int nw = w1 - w0 + 1;
-    int total = (r1 - r0) * nw;
-    u32* m = mask + (size_t)f * d.NW;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int totalw = (r1 - r0) * nw;
+    u32* m = mask + (size_t)flo * d.NW;
+    for (int i = lane_id(); i < totalw; i += 32) {
         int row = r0 + i / nw, w = w0 + i % nw;
         int lo = max(c0 - (w << 5), 0), hi = min(c1 - 1 - (w << 5), 31);
         atomicOr(&m[(size_t)(d.H - 1 - row) * d.WW + w], bit_range(lo, hi));

@@ -627,9 +627,8 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     CK(cudaMemsetAsync(h->hist, 0, (size_t)2 * h->B * 256 * sizeof(u32), s));
     if (mode == 0) {
         CK(cudaMemsetAsync(h->starmask, 0, (size_t)n * d.NW * sizeof(u32), s));
-        int maxr = 0;
-        for (int f = 0; f < n; f++) maxr = max(maxr, h->rect_off_h[f + 1] - h->rect_off_h[f]);
-        if (maxr > 0) { k_star_mask<<<dim3(maxr, n), 128, 0, s>>>(h->rects_d, h->rect_off_d, h->starmask, d); LAUNCH_CHECK(); }
+        const int total_rects = h->rect_off_h[n];
+        if (total_rects > 0) { k_star_mask<<<(total_rects + 3) / 4, 128, 0, s>>>(h->rects_d, h->rect_off_d, n, total_rects, h->starmask, d); LAUNCH_CHECK(); }
     }
     float* clipped = nullptr;
     if (want_clipped) {
