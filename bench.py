@@ -186,8 +186,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    per_step = max(2 * cores, 8)
-    frames, cats, _rects, _kinds = make_pool(min(per_step, 32), 0)
+    frames, cats, _rects, _kinds = make_pool(64, 0)      # the same 64-frame pool rank 0 of our arm uses
+    cal_value, _ = cpu_frames_per_s(frames, cats, max(2 * cores, 8), cores)
+    per_step = int(min(max(cal_value * 4.0, 2 * cores), 2048))   # ~4 s of all-core CPU work per step
     import multiprocessing as mp
     jobs = [(frames[i % len(frames)], cats[i % len(frames)], synth.FILTERS[i % 5]) for i in range(per_step)]
     with mp.get_context("fork").Pool(cores) as pool:
@@ -293,6 +294,7 @@ def run_ours(args):
                               "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "profile_only": True,
                               "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B},
                               "stages": [{"stage": n, "ms_per_step": ms / args.steps} for n, ms in stage_ms]}))
+        sampler.stop()
         return 0
 
     # ---- e2e: host frames -> device -> results, double-buffered over two handles -------------
@@ -372,10 +374,15 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": prep_bytes,
                 "note": "k_prep reads the float frame once (4N) and writes both passes' uint8 planes (2N); "
                         "traffic from profiles/ ncu capture when present"}
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
+    # dram__bytes_read.sum + dram__bytes_write.sum of k_prep per launch, from the newest committed ncu --set full capture
+    import glob
+    for tr_path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")), reverse=True):
         try:
-            roofline["traffic"] = json.load(open(tr_path)).get("k_prep_bytes_per_launch_b%d" % B)
+            t = json.load(open(tr_path))
+            if "k_prep_bytes_per_launch_b%d" % B in t:
+                roofline["traffic"] = t["k_prep_bytes_per_launch_b%d" % B]
+                roofline["traffic_source"] = "profiles/" + os.path.basename(tr_path)
+                break
         except Exception:
             pass
 
@@ -383,7 +390,9 @@ def run_ours(args):
     cores = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1:
-        sample = min(max(2 * cores, 8), 128)
+        # bounded sample: calibrate on 2 frames per core, then size the timed sample for ~12 s of wall clock
+        cal_value, _ = cpu_frames_per_s(frames, cats, max(2 * cores, 8), cores)
+        sample = int(min(max(cal_value * 12.0, 4 * cores), 4096))
         cpu_value, cpu_s = cpu_frames_per_s(frames, cats, sample, cores)
         import cv2
         cpu_baseline = {"value": cpu_value, "unit": "frames/s", "cores": cores, "kind": "port",

@@ -88,15 +88,6 @@ def _load_frame(run, camcol, filter, field):
             os.remove(fitspath)
 
 
-def _write_error(errors, run, camcol, filter, field, exc, debug):
-    """detecttrails.py:133-139."""
-    if debug:
-        traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
-    errors.write(f"{run} {camcol} {filter} {field}\n")
-    traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3, file=errors)
-    errors.write(str(exc) + "\n\n")
-
-
 _handles = {}
 
 
@@ -111,11 +102,19 @@ def _batch_handle(shape, batch, device):
     return h
 
 
-def process_fields(results, errors, frames, params_bright, params_dim, params_removestars, batch=16, device=0):
-    """Process an ordered list of (run, camcol, filter, field) in GPU batches; results/errors are written
-    in list order, exactly the lines the reference's per-frame loop would write."""
+def _error_text(run, camcol, filter, field, exc):
+    """The text detecttrails.py:133-139 appends to errors.txt for one failed frame."""
+    return (f"{run} {camcol} {filter} {field}\n" +
+            "".join(traceback.format_exception(type(exc), exc, exc.__traceback__, limit=3)) + str(exc) + "\n\n")
+
+
+def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0):
+    """Run an ordered list of (run, camcol, filter, field) through the GPU in batches.  Returns one record per
+    frame, in list order: ("line", results_line) for a detection, ("none", "") for no detection,
+    ("err", errors_text) for a failure - exactly what the reference's per-frame loop would append."""
     debug = bool(params_bright["debug"] or params_dim["debug"])
     frames = list(frames)
+    records = []
     for i0 in range(0, len(frames), batch):
         chunk = frames[i0:i0 + batch]
         loaded = []          # per frame: ("ok", img, rects, printit) or ("err", exc)
@@ -163,15 +162,47 @@ def process_fields(results, errors, frames, params_bright, params_dim, params_re
                     outcome[j] = ("err", e)
         for j, (run, camcol, filter, field) in enumerate(chunk):
             item = loaded[j]
-            if item[0] == "err":
-                _write_error(errors, run, camcol, filter, field, item[1], debug)
-                continue
-            o = outcome[j]
-            if o[0] == "err":
-                _write_error(errors, run, camcol, filter, field, o[1], debug)
-            elif o[1]:
-                res = o[2]
-                results.write(item[3] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n")
+            exc = item[1] if item[0] == "err" else (outcome[j][1] if outcome[j][0] == "err" else None)
+            if exc is not None:
+                if debug:
+                    traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
+                records.append(("err", _error_text(run, camcol, filter, field, exc)))
+            elif outcome[j][1]:
+                res = outcome[j][2]
+                records.append(("line", item[3] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n"))
+            else:
+                records.append(("none", ""))
+    return records
+
+
+def write_records(results, errors, records):
+    for kind, text in records:
+        if kind == "line":
+            results.write(text)
+        elif kind == "err":
+            errors.write(text)
+
+
+def process_fields(results, errors, frames, params_bright, params_dim, params_removestars, batch=16, device=0,
+                   distributed=None, compute=None):
+    """Process an ordered list of (run, camcol, filter, field); results/errors are written in list order,
+    exactly the lines the reference's per-frame loop would write.
+
+    With ``torch.distributed`` initialised (one process per GPU, e.g. under torchrun) the list is sharded by
+    frame across the ranks - blocks of ``batch`` consecutive frames dealt round-robin, no data-path collective -
+    and rank 0 gathers the per-frame records and writes them in the original order (lfd_b200/sharding.py).
+    ``distributed=False`` forces the single-process path; ``compute`` replaces the GPU stage (tests)."""
+    from . import sharding
+    compute = compute or (lambda fr: compute_fields(fr, params_bright, params_dim, params_removestars, batch=batch, device=device))
+    frames = list(frames)
+    if distributed is None:
+        distributed = sharding.is_distributed()
+    if not distributed:
+        write_records(results, errors, compute(frames))
+        return
+    merged = sharding.run_sharded(frames, compute, block=batch)
+    if merged is not None:          # rank 0
+        write_records(results, errors, merged)
 
 
 def process_field(results, errors, run, camcol, filter, field, params_bright, params_dim, params_removestars):

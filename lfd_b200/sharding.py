@@ -1,0 +1,55 @@
+"""Frame sharding across GPUs: frames are independent, so the ordered frame list is dealt to
+the ranks in blocks and only the per-frame result records (<= ~100 bytes each) travel back - a host-side ordered
+gather on rank 0, no collective on the data path and no NVLink traffic.
+
+This replaces the reference's only scale-out story, hand-submitted PBS jobs whose results.txt files are
+concatenated afterwards (/root/reference/lfd/createjobs/createjobs.py:173-218, lfd/createjobs/generic), and keeps
+what those jobs cannot: results.txt / errors.txt in exactly the order a sequential run writes them
+(/root/reference/lfd/detecttrails/detecttrails.py:349-407)."""
+
+
+def is_distributed():
+    try:
+        import torch.distributed as dist
+    except ImportError:      # pragma: no cover
+        return False
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_indices(n, rank, world, block):
+    """Indices of the frames rank `rank` processes: blocks of `block` consecutive frames, round-robin over ranks
+    (full GPU batches, and neighbouring fields - which share catalog/FITS directories - stay together)."""
+    block = max(int(block), 1)
+    out = []
+    for b0 in range(rank * block, n, world * block):
+        out.extend(range(b0, min(b0 + block, n)))
+    return out
+
+
+def merge_records(n, parts):
+    """parts: iterable of (indices, records) per rank -> the n records in frame order."""
+    merged = [None] * n
+    for idxs, recs in parts:
+        if len(idxs) != len(recs):
+            raise ValueError("a rank returned %d records for %d frames" % (len(recs), len(idxs)))
+        for i, r in zip(idxs, recs):
+            if merged[i] is not None:
+                raise ValueError("frame %d was processed twice" % i)
+            merged[i] = r
+    missing = [i for i, r in enumerate(merged) if r is None]
+    if missing:
+        raise ValueError("frames %s were not processed by any rank" % missing[:8])
+    return merged
+
+
+def run_sharded(frames, compute, block=16, group=None):
+    """Each rank runs compute(its frames) and rank 0 returns the merged, ordered record list (other ranks: None)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    idxs = shard_indices(len(frames), rank, world, block)
+    recs = compute([frames[i] for i in idxs])
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((idxs, recs), gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    return merge_records(len(frames), gathered)

@@ -20,7 +20,7 @@ P = os.path.join(ROOT, "profiles")
 lines = [l for l in open(launches) if l.startswith('"')]
 tot, cnt = collections.Counter(), collections.Counter()
 for row in csv.DictReader(lines):
-    name = re.sub(r"\(.*", "", row["Kernel Name"])
+    name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
     tot[name] += float(row["Metric Value"])
     cnt[name] += 1
 T = sum(tot.values())
@@ -64,7 +64,7 @@ mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tr = {}
 ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 for r in data:
-    name = r[hdr.index("Kernel Name")].split("(")[0]
+    name = re.sub(r"<.*", "", r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")).strip()
     tr.setdefault(name, []).append(float(r[ir]) * mul[units[ir]] + float(r[iw]) * mul[units[iw]])
 traffic = {"batch": batch, "source": os.path.basename(raw), "unit": "bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch"}
 for k, v in tr.items():

@@ -1,0 +1,75 @@
+"""CPU tests of the N>1 host path: frame sharding + ordered gather over torch.distributed (gloo, world_size 2).
+The GPU stage is replaced by a deterministic stand-in (`compute=`), so this checks exactly the logic that
+differs from the single-GPU path: which rank gets which frames, and that rank 0 writes results.txt / errors.txt
+in the order a sequential run would (detecttrails.py:349-407)."""
+import io
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from lfd_b200 import sharding
+
+
+def test_shard_indices_partition():
+    for n in (0, 1, 5, 16, 33, 100):
+        for world in (1, 2, 3, 8):
+            for block in (1, 4, 16):
+                parts = [sharding.shard_indices(n, r, world, block) for r in range(world)]
+                flat = sorted(i for p in parts for i in p)
+                assert flat == list(range(n))
+                for p in parts:
+                    assert p == sorted(p)
+                # consecutive frames of a block stay on one rank
+                for r, p in enumerate(parts):
+                    for i in p:
+                        assert (i // block) % world == r
+
+
+def test_merge_records_detects_holes_and_duplicates():
+    assert sharding.merge_records(3, [([0, 2], ["a", "c"]), ([1], ["b"])]) == ["a", "b", "c"]
+    with pytest.raises(ValueError):
+        sharding.merge_records(3, [([0, 2], ["a", "c"])])
+    with pytest.raises(ValueError):
+        sharding.merge_records(2, [([0, 1], ["a", "b"]), ([1], ["b"])])
+
+
+def _fake_compute(frames):
+    out = []
+    for (run, camcol, flt, field) in frames:
+        if field % 7 == 0:
+            out.append(("err", "%d %d %s %d\nboom\n\n" % (run, camcol, flt, field)))
+        elif field % 3 == 0:
+            out.append(("line", "%d %d %s %d 1 2 3 4\n" % (run, camcol, flt, field)))
+        else:
+            out.append(("none", ""))
+    return out
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from lfd_b200.detecttrails import process_fields
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        frames = [(2888, 1, "r", f) for f in range(100, 137)]
+        res, err = io.StringIO(), io.StringIO()
+        process_fields(res, err, frames, {"debug": False}, {"debug": False}, {}, batch=4, compute=_fake_compute)
+        with open(os.path.join(tmp, "out%d.txt" % rank), "w") as f:
+            f.write(res.getvalue() + "---\n" + err.getvalue())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_ordered_gather(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    frames = [(2888, 1, "r", f) for f in range(100, 137)]
+    recs = _fake_compute(frames)
+    exp = "".join(t for k, t in recs if k == "line") + "---\n" + "".join(t for k, t in recs if k == "err")
+    assert (tmp_path / "out0.txt").read_text() == exp          # rank 0 wrote everything, in sequential order
+    assert (tmp_path / "out1.txt").read_text() == "---\n"      # other ranks write nothing
