@@ -73,8 +73,13 @@ k_rects(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const CclBuf* 
 #define RECT_SMALL_PTS 128          // hull capacity of the warp path's shared-memory tier
 #define RECT_T_ROWS 64              // thread path: contours of at most this many rows ...
 #define RECT_T_PTS 40               // ... whose monotone-chain stack never exceeds this (else: warp path)
-#define RECT_R_STRIDE 33            // row-extreme staging [RECT_T_ROWS][33]: conflict-free for both access patterns
-#define RECT_WARP_WORDS (RECT_T_PTS * 32 + RECT_T_ROWS * RECT_R_STRIDE)   // per-warp shared memory (u32 words)
+#define RECT_TPW 8                  // thread-path contours per warp: the kernel is bound by the serial latency of one
+                                    // contour, not by issue slots, so 8 busy lanes x 4 times as many warps beats 32 x 1
+#define RECT_R_STRIDE (RECT_TPW + 1) // row-extreme staging [RECT_T_ROWS][RECT_TPW + 1]: conflict-free both ways
+#define RECT_WARP_WORDS_T (RECT_T_PTS * RECT_TPW + RECT_T_ROWS * RECT_R_STRIDE)
+#define RECT_WARP_WORDS_W (6 * RECT_SMALL_PTS + 8)                    // warp path: A, B, vect(2), inv, rows
+#define RECT_TALL_PTS 448           // warp path, tall contours: capacity of each packed partial-chain list
+#define RECT_WARP_WORDS (RECT_WARP_WORDS_T > RECT_WARP_WORDS_W ? RECT_WARP_WORDS_T : RECT_WARP_WORDS_W)
 
 __host__ __device__ inline size_t rects_smem(int nframes) { return (size_t)RECT_WARPS * RECT_WARP_WORDS * 4 + ((size_t)nframes + 1) * 4; }
 
@@ -150,7 +155,7 @@ __device__ __forceinline__ void emit_rect(const lfdgeom::Rect& r, int e, int kin
 // stay converged (a return inside the loops left them running one after the other).
 __device__ __forceinline__ bool rect_thread_path(const u32* R, int hh, int y0, u32* T, u32 mask, lfdgeom::Rect* out)
 {
-    Chain ch; ch.init(T, 32);
+    Chain ch; ch.init(T, RECT_TPW);
     bool ovf = false;
     for (int r = 0; r < hh; r++) {
         u32 v = R[r * RECT_R_STRIDE];
@@ -175,7 +180,7 @@ __device__ __forceinline__ bool rect_thread_path(const u32* R, int hh, int y0, u
             if (a != b) ch.push(pt_pack(a, y0 + r), lo);
         }
         n = ch.k - 1;                                          // the last point equals T[0]
-        if (n == 2 && T[0] == T[32]) n = 1;
+        if (n == 2 && T[0] == T[RECT_TPW]) n = 1;
     }
     if (ovf) n = 0;
     __syncwarp(mask);
@@ -184,14 +189,14 @@ __device__ __forceinline__ bool rect_thread_path(const u32* R, int hh, int y0, u
         u32 best = 0;
         int lx = 0, rx = 0, ty = 0, by = 0;
         for (int j = 0; j < n; j++) {
-            u32 v = T[j * 32];
+            u32 v = T[j * RECT_TPW];
             u32 key = ((v & 0xffffu) << 16) | (v >> 16);       // x, then y
             if (j == 0 || key > best) { best = key; start = j; }
         }
         // extremes in caliper order (index relative to start): first index of min x / max x / max y / min y
         for (int j = 0; j < n; j++) {
             int q = j + start; if (q >= n) q -= n;
-            lfdgeom::Pt p = pt_unpack(T[q * 32]);
+            lfdgeom::Pt p = pt_unpack(T[q * RECT_TPW]);
             if (j == 0) { lx = rx = p.x; ty = by = p.y; }
             if (p.x < lx) { lx = p.x; left = j; }
             if (p.x > rx) { rx = p.x; right = j; }
@@ -200,7 +205,7 @@ __device__ __forceinline__ bool rect_thread_path(const u32* R, int hh, int y0, u
         }
     }
     __syncwarp(mask);
-    PackedHull hp; hp.a = T; hp.n = n; hp.start = start; hp.stride = 32;
+    PackedHull hp; hp.a = T; hp.n = n; hp.start = start; hp.stride = RECT_TPW;
     if (n <= 2) {
         lfdgeom::Pt z; z.x = 0; z.y = 0;
         lfdgeom::min_area_rect_small(n, n > 0 ? hp(0) : z, n > 1 ? hp(1) : z, out);
@@ -224,7 +229,8 @@ __device__ __forceinline__ void rect_warp_path(const int* __restrict__ rmin, con
     int* sRow = reinterpret_cast<int*>(sI + RECT_SMALL_PTS + 2);
     u32 *A, *B;
     float *vect, *inv;
-    if (2 * hh <= RECT_SMALL_PTS) {
+    const bool tall = 2 * hh > RECT_SMALL_PTS;
+    if (!tall) {
         A = sA; B = sB; vect = sV; inv = sI;
         for (int r = lane; r < hh; r += 32) { sRow[r] = rmin[r]; sRow[RECT_SMALL_PTS / 2 + r] = rmax[r]; }
         __syncwarp();
@@ -257,27 +263,72 @@ __device__ __forceinline__ void rect_warp_path(const int* __restrict__ rmin, con
     }
     __syncwarp();
     // level 2: lane 0 merges the ascending chains, lane 1 the descending ones (same instruction stream)
-    Chain cm; cm.init(lane == 1 ? B : A, 1);
-    for (int t = 0; t < 32; t++) {
-        int na_t = __shfl_sync(FULLMASK, ka, t), nb_t = __shfl_sync(FULLMASK, kb, 31 - t);
-        if (lane < 2) {
-            int L = lane ? 31 - t : t;
-            int q0 = min(L * c, hh), q1 = min(q0 + c, hh);
-            const u32* src = lane ? B + 2 * (hh - q1) : A + 2 * q0;
-            int cnt = lane ? nb_t : na_t;
-            for (int j = 0; j < cnt; j++) cm.push(src[j], 2);
+    int KA, KB;
+    u32 *HA = A, *HB = B;
+    bool compacted = false;
+    if (tall) {
+        // partial chains of a tall contour live in global scratch; they are short, so pack them into the warp's
+        // shared memory first: the serial merge then runs at shared-memory latency
+        int ia = ka, ib = kb;
+        for (int o = 1; o < 32; o <<= 1) {
+            int va = __shfl_up_sync(FULLMASK, ia, o), vb = __shfl_down_sync(FULLMASK, ib, o);
+            if (lane >= o) ia += va;
+            if (lane + o < 32) ib += vb;
+        }
+        const int suma = __shfl_sync(FULLMASK, ia, 31), sumb = __shfl_sync(FULLMASK, ib, 0);
+        if (suma <= RECT_TALL_PTS && sumb <= RECT_TALL_PTS) {
+            compacted = true;
+            u32* SA = wsm; u32* SB = wsm + RECT_TALL_PTS;
+            const u32* ga = A + 2 * r0; const u32* gb = B + 2 * (hh - r1);
+            for (int j = 0; j < ka; j++) SA[ia - ka + j] = ga[j];
+            for (int j = 0; j < kb; j++) SB[ib - kb + j] = gb[j];       // lanes 31..0 in this order
+            __syncwarp();
+            Chain cm; cm.init(lane == 1 ? SB : SA, 1);
+            if (lane < 2) {
+                const u32* src = lane ? SB : SA;
+                const int cnt = lane ? sumb : suma;
+                for (int j = 0; j < cnt; j++) cm.push(src[j], 2);
+            }
+            KA = __shfl_sync(FULLMASK, cm.k, 0); KB = __shfl_sync(FULLMASK, cm.k, 1);
+            HA = SA; HB = SB;
         }
     }
-    const int KA = __shfl_sync(FULLMASK, cm.k, 0), KB = __shfl_sync(FULLMASK, cm.k, 1);
+    if (!compacted) {
+        Chain cm; cm.init(lane == 1 ? B : A, 1);
+        for (int t = 0; t < 32; t++) {
+            int na_t = __shfl_sync(FULLMASK, ka, t), nb_t = __shfl_sync(FULLMASK, kb, 31 - t);
+            if (lane < 2) {
+                int L = lane ? 31 - t : t;
+                int q0 = min(L * c, hh), q1 = min(q0 + c, hh);
+                const u32* src = lane ? B + 2 * (hh - q1) : A + 2 * q0;
+                int cnt = lane ? nb_t : na_t;
+                for (int j = 0; j < cnt; j++) cm.push(src[j], 2);
+            }
+        }
+        KA = __shfl_sync(FULLMASK, cm.k, 0); KB = __shfl_sync(FULLMASK, cm.k, 1);
+    }
     const int n = (KA <= 1) ? KA : KA + KB - 2;
     __syncwarp();
-    // gather the hull (A chain, then the interior of the B chain); small hulls of tall contours move to
-    // shared memory so that the serial caliper loop never waits on global memory
-    if (2 * hh > RECT_SMALL_PTS && n <= RECT_SMALL_PTS) {
-        for (int j = lane; j < n; j += 32) sA[j] = j < KA ? A[j] : B[1 + j - KA];
+    // gather the hull (A chain, then the interior of the B chain).  Hulls of up to RECT_SMALL_PTS vertices -
+    // all but pathological ones - go to shared memory, so the serial caliper loop never waits on global memory.
+    if (n <= RECT_SMALL_PTS) {
+        u32 tmp[RECT_SMALL_PTS / 32];
+#pragma unroll
+        for (int k = 0; k < RECT_SMALL_PTS / 32; k++) {
+            int j = lane + 32 * k;
+            tmp[k] = j < n ? (j < KA ? HA[j] : HB[1 + j - KA]) : 0u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RECT_SMALL_PTS / 32; k++) {
+            int j = lane + 32 * k;
+            if (j < n) sA[j] = tmp[k];
+        }
         A = sA; vect = sV; inv = sI;
     } else {
-        for (int j = lane; j < KB - 2; j += 32) A[KA + j] = B[1 + j];
+        // (only reachable for tall contours: A, vect, inv are the global scratch)
+        if (compacted) { for (int j = lane; j < KA; j += 32) A[j] = HA[j]; }
+        for (int j = lane; j < KB - 2; j += 32) A[KA + j] = HB[1 + j];
     }
     __syncwarp();
     // caliper start vertex: lexicographic maximum (x, then y)
@@ -340,9 +391,9 @@ k_rects_warp(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const Ccl
     }
     __syncthreads();
     const int total_all = pre[nframes];
-    for (int base = (blockIdx.x * RECT_WARPS + warp) * 32; base < total_all; base += gridDim.x * RECT_WARPS * 32) {
+    for (int base = (blockIdx.x * RECT_WARPS + warp) * RECT_TPW; base < total_all; base += gridDim.x * RECT_WARPS * RECT_TPW) {
         const int task = base + lane;
-        const bool valid = task < total_all;
+        const bool valid = lane < RECT_TPW && task < total_all;
         int f = 0, e = 0, kind = 0, hh = 0, slot = 0, ho = 0, y0 = 0;
         if (valid) {
             int flo = 0, fhi = nframes;           // largest f with pre[f] <= task
@@ -359,8 +410,8 @@ k_rects_warp(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const Ccl
         bool small = valid && hh <= RECT_T_ROWS;
         __syncwarp();
         // stage the row extremes of the 32 contours with coalesced loads: contour l -> column l of R
-        u32* Rw = wsm + RECT_T_PTS * 32;
-        for (int l = 0; l < 32; l++) {
+        u32* Rw = wsm + RECT_T_PTS * RECT_TPW;
+        for (int l = 0; l < RECT_TPW; l++) {
             const int hl = __shfl_sync(FULLMASK, small ? hh : 0, l);
             if (hl == 0) continue;
             const int fl = __shfl_sync(FULLMASK, f, l), sl = __shfl_sync(FULLMASK, slot, l);

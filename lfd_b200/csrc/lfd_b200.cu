@@ -590,7 +590,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 4], s));
     // rectangles + box image
-    k_rects_warp<<<148 * 4, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], h->ctl, pass, d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 5], s));
