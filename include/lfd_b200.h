@@ -63,6 +63,7 @@ extern "C" {
 #define LFD_INPUT_BIGENDIAN 1   /* raw FITS payload: big-endian float32, byte-swapped on the device */
 #define LFD_KEEP_TAPS 2         /* materialise the uint8 stage images for lfd_get_stage */
 #define LFD_FULL_LINES 4        /* sort and keep the full HoughLines lists (taps / parity) */
+#define LFD_SERIAL_PASSES 8     /* run the dim pass after the bright pass on one stream (per-stage timings) */
 
 /* stage ids for lfd_get_stage (uint8 H*W unless noted) */
 enum lfd_stage {

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 LFD_OK, LFD_E_ARG, LFD_E_CUDA, LFD_E_UNSUPPORTED, LFD_E_CAPACITY, LFD_E_STATE = 0, -1, -2, -3, -4, -5
 FRAME_OVERFLOW, FRAME_NO_LINES_EQU, FRAME_NO_LINES_BOX = 1, 2, 4
 PASS_BRIGHT, PASS_DIM = 0, 1
-INPUT_NATIVE, INPUT_BIGENDIAN, KEEP_TAPS, FULL_LINES = 0, 1, 2, 4
+INPUT_NATIVE, INPUT_BIGENDIAN, KEEP_TAPS, FULL_LINES, SERIAL_PASSES = 0, 1, 2, 4, 8
 MAX_SET_LINES = 16
 
 STAGES = {"mask": 0, "gray": 1, "equ": 2, "eroded": 3, "morph": 4, "canny": 5, "box": 6, "hist": 7, "lut": 8,

@@ -27,7 +27,7 @@ struct FrameCtl {
     int npeaks[2];        // Hough peaks: equ / box
     int nnz[2];           // non-zero pixels voted: equ / box
     int status;           // LFD_FRAME_* bits
-    int pad;
+    int detected;         // this pass accepted a line (k_check_theta)
     int ncomp_saved[2][2]; // [pass][kind] contour counts kept for the RECTS tap
 };
 

@@ -292,13 +292,7 @@ __global__ void k_check_theta(lfd_result* __restrict__ res, FrameCtl* __restrict
             detected = !reject;
         }
     }
-    if (detected) {
-        R->detected = 1;
-        R->pass = pass;
-        R->rho = R->top_equ[pass][0][0];
-        R->theta = R->top_equ[pass][0][1];
-    }
-    R->status = ctl[f].status;
-    // the dim pass only runs when bright did not detect (detecttrails.py:126-129)
-    if (pass == 0) ctl[f].active[1] = (detected || (ctl[f].status & (LFD_FRAME_NO_LINES_EQU | LFD_FRAME_NO_LINES_BOX | LFD_FRAME_OVERFLOW))) ? 0 : ctl[f].active[1];
+    // the frame's verdict (which pass counts, rho/theta, status) is assembled by k_finalize: the two passes run
+    // concurrently and only write their own fields
+    ctl[f].detected = detected ? 1 : 0;
 }

@@ -53,7 +53,9 @@ struct lfd_handle {
     lfd_config cfg;
     lfd_params params;
     bool have_params = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // uploads, prep, bright pass, results
+    cudaStream_t stream2 = nullptr;       // dim pass, overlapped with the bright pass
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int64_t launches = 0;
     int last_n = 0, last_flags = 0;
@@ -78,15 +80,15 @@ struct lfd_handle {
     u8* nms_tap[2] = {nullptr, nullptr};
     float* clipped = nullptr;         // [N] lazily (run_pass writeback)
     int* labels_tap = nullptr;        // [N] lazily
-    FrameCtl* ctl = nullptr;          // [B]
+    FrameCtl* ctl = nullptr;          // [2][B]: one bookkeeping block per pass (the passes run concurrently)
     lfd_result* res_d = nullptr;      // [B]
     int64_t* counters_d = nullptr;    // [16]
-    uint2* segs = nullptr;            // [B][2][NW]
-    CclBuf* ccl_d[2] = {nullptr, nullptr};   // [B] per kind
-    CompBuf* comp_d = nullptr;               // [B]
-    RectBuf* rbuf_d[2] = {nullptr, nullptr}; // [B] per pass
-    std::vector<CclBuf> ccl_h[2];
-    std::vector<CompBuf> comp_h;
+    uint2* segs[2] = {nullptr, nullptr};     // per pass: [B][2][NW]
+    CclBuf* ccl_d[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [pass][kind] -> [B]
+    CompBuf* comp_d[2] = {nullptr, nullptr}; // per pass: [B]
+    RectBuf* rbuf_d[2] = {nullptr, nullptr}; // per pass: [B]
+    std::vector<CclBuf> ccl_h[2][2];
+    std::vector<CompBuf> comp_h[2];
     std::vector<RectBuf> rbuf_h[2];
     std::vector<void*> allocs;
     HoughBufs hb[2];
@@ -96,7 +98,7 @@ struct lfd_handle {
     lfd_result* res_h = nullptr;      // pinned [B]
     int4* rects_h = nullptr;          // pinned
     int* rect_off_h = nullptr;        // pinned
-    FrameCtl* ctl_h = nullptr;        // pinned [B]
+    FrameCtl* ctl_h = nullptr;        // pinned [2][B]
     int64_t* counters_h = nullptr;    // pinned [16] (a pageable destination would make the D2H copy block the host)
 
     cudaEvent_t ev[N_TIMINGS + 1];
@@ -156,7 +158,8 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // ------------------------------------------------------------------------------------------------
 // small bookkeeping kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ctl_init(FrameCtl* ctl, lfd_result* res, int n, int act0, int act1)
+// ctl: [2][B] (one block per pass); block p only ever looks at active[p] / hough[p]
+__global__ void k_ctl_init(FrameCtl* ctl, int B, lfd_result* res, int n, int act0, int act1)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
@@ -164,6 +167,7 @@ __global__ void k_ctl_init(FrameCtl* ctl, lfd_result* res, int n, int act0, int 
     memset(&c, 0, sizeof(c));
     c.active[0] = act0; c.active[1] = act1;
     ctl[f] = c;
+    ctl[B + f] = c;
     lfd_result r;
     memset(&r, 0, sizeof(r));
     r.pass = -1;
@@ -195,9 +199,41 @@ __global__ void k_pass_end(FrameCtl* ctl, int n, int pass, int numangle, unsigne
     atomicAdd(&counters[4], (unsigned long long)c->nruns[1]);
     atomicAdd(&counters[5], (unsigned long long)(c->ncomp[0] + c->ncomp[1]));
     atomicAdd(&counters[6], (unsigned long long)c->npass);
-    if (pass == 1) atomicAdd(&counters[7], 1ull);
     if (c->hough[pass]) atomicAdd(&counters[8], 1ull);
     atomicAdd(&counters[9 + pass], 1ull);
+}
+
+// Verdict of the frame from the two passes' private results (detecttrails.py:125-131): bright wins; the dim
+// pass counts only where bright neither detected nor failed, and is reported as "not run" elsewhere.
+// mode 0: both passes ; 1: bright only ; 2: dim only
+__global__ void k_finalize(const FrameCtl* __restrict__ ctl, int B, lfd_result* __restrict__ res, int n, int mode,
+                           unsigned long long* counters)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const FrameCtl& c0 = ctl[f];
+    const FrameCtl& c1 = ctl[B + f];
+    lfd_result* R = res + f;
+    const int errbits = LFD_FRAME_NO_LINES_EQU | LFD_FRAME_NO_LINES_BOX | LFD_FRAME_OVERFLOW;
+    const bool ran0 = mode != 2, ran1 = mode != 1;
+    const bool use1 = ran1 && !(ran0 && (c0.detected || (c0.status & errbits)));
+    int status = ran0 ? c0.status : 0;
+    if (use1) status |= c1.status;
+    R->status = status;
+    int pass = -1;
+    if (ran0 && c0.detected) pass = 0;
+    else if (use1 && c1.detected) pass = 1;
+    R->detected = pass >= 0;
+    R->pass = pass;
+    if (pass >= 0) { R->rho = R->top_equ[pass][0][0]; R->theta = R->top_equ[pass][0][1]; }
+    if (ran1 && !use1) {      // what a run that skipped the dim pass reports
+        R->rect_detection[1] = -1; R->n_lines_equ[1] = -1; R->n_lines_box[1] = -1; R->rejected[1] = 0;
+        for (int i = 0; i < LFD_MAX_SET_LINES; i++) {
+            R->top_equ[1][i][0] = R->top_equ[1][i][1] = 0.f;
+            R->top_box[1][i][0] = R->top_box[1][i][1] = 0.f;
+        }
+    }
+    if (mode == 0 && use1) atomicAdd(&counters[7], 1ull);
 }
 
 __global__ void k_pack_mask(const u8* __restrict__ img, u32* __restrict__ mask, Dims d)
@@ -300,6 +336,7 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (!h) return LFD_E_ARG;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
     for (void* p : h->allocs) cudaFree(p);
     for (int p = 0; p < 2; p++) {
         if (h->hb[p].accum) cudaFree(h->hb[p].accum);
@@ -315,6 +352,9 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->counters_h) cudaFreeHost(h->counters_h);
     for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; i++) if (h->mark_valid[i]) cudaEventDestroy(h->mark[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return LFD_OK;
@@ -342,6 +382,9 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     long long worst = (long long)H * ((W + 1) / 2);
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
     CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_smem(max_batch)));
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
@@ -367,48 +410,49 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
         DA(h->box[p], (size_t)B * NW);
     }
     DA(h->tap_u8, N);
-    DA(h->ctl, (size_t)B);
+    DA(h->ctl, (size_t)2 * B);
     DA(h->res_d, (size_t)B);
     DA(h->counters_d, 16);
-    DA(h->segs, (size_t)B * 2 * NW);
+    DA(h->segs[0], (size_t)B * 2 * NW);
+    DA(h->segs[1], (size_t)B * 2 * NW);
     const int MR = h->cfg.max_runs, MC = h->cfg.max_components;
     const int slotcap = 2 * MR + 4 * MC, hullcap = 2 * slotcap + 4 * MC;
-    // one slab per field, sliced per frame
+    // one slab per field, sliced per frame; everything the two passes touch exists once per pass
+    for (int p = 0; p < 2; p++)
     for (int k = 0; k < 2; k++) {
-        h->ccl_h[k].resize(B);
+        h->ccl_h[p][k].resize(B);
         Run* runs; int *parent, *flag, *ymax, *compidx, *rowbase, *rowcnt; u16* wpre;
         DA(runs, (size_t)B * MR); DA(parent, (size_t)B * MR); DA(flag, (size_t)B * MR); DA(ymax, (size_t)B * MR);
         DA(compidx, (size_t)B * MR); DA(rowbase, (size_t)B * (H + 1)); DA(wpre, (size_t)B * NW); DA(rowcnt, (size_t)B * H);
         for (int f = 0; f < B; f++) {
-            CclBuf& c = h->ccl_h[k][f];
+            CclBuf& c = h->ccl_h[p][k][f];
             c.runs = runs + (size_t)f * MR; c.parent = parent + (size_t)f * MR; c.flag = flag + (size_t)f * MR;
             c.ymax = ymax + (size_t)f * MR; c.compidx = compidx + (size_t)f * MR;
             c.rowbase = rowbase + (size_t)f * (H + 1); c.wpre = wpre + (size_t)f * NW; c.rowcnt = rowcnt + (size_t)f * H;
         }
-        DA(h->ccl_d[k], (size_t)B);
-        CK(cudaMemcpy(h->ccl_d[k], h->ccl_h[k].data(), B * sizeof(CclBuf), cudaMemcpyHostToDevice));
+        DA(h->ccl_d[p][k], (size_t)B);
+        CK(cudaMemcpy(h->ccl_d[p][k], h->ccl_h[p][k].data(), B * sizeof(CclBuf), cudaMemcpyHostToDevice));
     }
-    h->comp_h.resize(B);
-    {
+    for (int p = 0; p < 2; p++) {
+        h->comp_h[p].resize(B);
         int *root, *y0, *hh, *slot, *hulloff, *rowmin, *rowmax;
         DA(root, (size_t)B * 2 * MC); DA(y0, (size_t)B * 2 * MC); DA(hh, (size_t)B * 2 * MC);
         DA(slot, (size_t)B * 2 * MC); DA(hulloff, (size_t)B * 2 * MC);
         DA(rowmin, (size_t)B * slotcap); DA(rowmax, (size_t)B * slotcap);
         for (int f = 0; f < B; f++) {
-            CompBuf& c = h->comp_h[f];
+            CompBuf& c = h->comp_h[p][f];
             c.root = root + (size_t)f * 2 * MC; c.y0 = y0 + (size_t)f * 2 * MC; c.h = hh + (size_t)f * 2 * MC;
             c.slot = slot + (size_t)f * 2 * MC; c.hulloff = hulloff + (size_t)f * 2 * MC;
             c.rowmin = rowmin + (size_t)f * slotcap; c.rowmax = rowmax + (size_t)f * slotcap;
             c.slotcap = slotcap; c.hullcap = hullcap; c.maxcomp = MC;
         }
+        DA(h->comp_d[p], (size_t)B);
+        CK(cudaMemcpy(h->comp_d[p], h->comp_h[p].data(), B * sizeof(CompBuf), cudaMemcpyHostToDevice));
     }
-    DA(h->comp_d, (size_t)B);
-    CK(cudaMemcpy(h->comp_d, h->comp_h.data(), B * sizeof(CompBuf), cudaMemcpyHostToDevice));
-    // hull scratch is shared by both passes; rect lists are per pass
-    lfdgeom::Pt* hulls; float* hullfs;
-    DA(hulls, (size_t)B * hullcap); DA(hullfs, (size_t)B * 3 * hullcap);
     for (int p = 0; p < 2; p++) {
         h->rbuf_h[p].resize(B);
+        lfdgeom::Pt* hulls; float* hullfs;
+        DA(hulls, (size_t)B * hullcap); DA(hullfs, (size_t)B * 3 * hullcap);
         lfd_rect* rects; int* passing;
         DA(rects, (size_t)B * 2 * MC); DA(passing, (size_t)B * 2 * MC);
         for (int f = 0; f < B; f++) {
@@ -424,7 +468,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     CK(cudaMallocHost((void**)&h->res_h, (size_t)B * sizeof(lfd_result)));
     CK(cudaMallocHost((void**)&h->rects_h, (size_t)B * h->cfg.max_star_rects * sizeof(int4)));
     CK(cudaMallocHost((void**)&h->rect_off_h, ((size_t)B + 1) * sizeof(int)));
-    CK(cudaMallocHost((void**)&h->ctl_h, (size_t)B * sizeof(FrameCtl)));
+    CK(cudaMallocHost((void**)&h->ctl_h, (size_t)2 * B * sizeof(FrameCtl)));
     CK(cudaMemset(h->counters_d, 0, 16 * sizeof(int64_t)));
     CK(cudaMallocHost((void**)&h->counters_h, 16 * sizeof(int64_t)));
     memset(h->counters_h, 0, 16 * sizeof(int64_t));
@@ -505,11 +549,11 @@ extern "C" int lfd_set_params(lfd_handle* h, const lfd_params* p)
 // ------------------------------------------------------------------------------------------------
 // the pipeline
 // ------------------------------------------------------------------------------------------------
-static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
+static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStream_t s)
 {
     const Dims d = h->d;
     const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
-    cudaStream_t s = h->stream;
+    FrameCtl* const C = h->ctl + (size_t)pass * h->B;      // this pass's bookkeeping block
     const bool taps = flags & LFD_KEEP_TAPS;
     const int tbase = 2 + pass * (T_PER_PASS - 1);   // event index preceding this pass's first stage
     HoughBufs& hb = h->hb[pass];
@@ -517,9 +561,9 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
-    k_pass_begin<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, n); LAUNCH_CHECK();
+    k_pass_begin<<<(n + 127) / 128, 128, 0, s>>>(C, n); LAUNCH_CHECK();
     // LUT + morphology
-    k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist, h->lut, h->ctl, h->B, d.N, pass); LAUNCH_CHECK();
+    k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist, h->lut, C, h->B, d.N, pass); LAUNCH_CHECK();
     MorphCfg mc;
     mc.eh = pass ? pp.erode_h : 0; mc.ew = pass ? pp.erode_w : 0; mc.dh = pp.dilate_h; mc.dw = pp.dilate_w;
     u8* etap = nullptr;
@@ -536,7 +580,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
 #define MORPH_CASE(EH_, EW_, DH_, DW_)                                                                              \
         if (!done && (d.W % 8) == 0 && mc.eh == EH_ && mc.ew == EW_ && mc.dh == DH_ && mc.dw == DW_) {                \
             k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, \
-                                                               h->ctl, pass, d, nstrips, nunits);                    \
+                                                               C, pass, d, nstrips, nunits);                    \
             done = true;                                                                                             \
         }
         MORPH_CASE(0, 0, 4, 4)      // params_bright default (detecttrails.py:204)
@@ -547,7 +591,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
 #undef MORPH_CASE
         if (!done) {                // any other all-ones rectangle: shared-memory tile kernel
             dim3 mg((d.W + MORPH_TW - 1) / MORPH_TW, (d.H + MORPH_TH - 1) / MORPH_TH, n);
-            k_morph<<<mg, 256, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, h->ctl, pass, d, mc);
+            k_morph<<<mg, 256, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, C, pass, d, mc);
         }
         LAUNCH_CHECK();
     }
@@ -562,54 +606,54 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags)
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
         dim3 gg((nunits + 3) / 4, n);
-        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, nstrips, nunits, 0, 255);
-        else k_nms_march<false><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, nstrips, nunits, 0, 255);
+        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, nstrips, nunits, 0, 255);
+        else k_nms_march<false><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, nstrips, nunits, 0, 255);
     } else {
         dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
-        k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, h->ctl, pass, d, 0, 255);
+        k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, 0, 255);
     }
     LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 2], s));
     // foreground runs: hysteresis + outer contours
-    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[0], h->ctl, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[0], h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->edges[pass], h->ctl, pass, d); LAUNCH_CHECK();
-    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[0], h->comp_d, h->ctl, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[0], h->comp_d, h->ctl, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][0], C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], C, pass, d); LAUNCH_CHECK();
+    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 3], s));
     // background runs: hole contours
-    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[1], h->ctl, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[1], h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[1], h->comp_d, h->ctl, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][1], C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 4], s));
     // rectangles + box image
-    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d, h->rbuf_d[pass], h->ccl_d[0], h->ccl_d[1], h->ctl, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d[pass], h->rbuf_d[pass], h->ccl_d[pass][0], h->ccl_d[pass][1], C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
-    k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], h->ctl, pass, d); LAUNCH_CHECK();
+    k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], C, pass, d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 5], s));
     // Hough on the morphology output and on the box image
     CK(cudaMemsetAsync(hb.accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
-    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs, h->ctl, pass, d, (size_t)d.NW); LAUNCH_CHECK();
-    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs, hb.accum, hb.tabSin, hb.tabCos, h->ctl, pass,
+    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs[pass], C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
+    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs[pass], hb.accum, hb.tabSin, hb.tabCos, C, pass,
                                                                             hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
     int cells = hb.hc.numangle * hb.hc.numrho;
     int pblocks = (cells + 255) / 256; if (pblocks > 64) pblocks = 64;
-    k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(hb.accum, hb.keys, h->ctl, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
-    k_hough_topk<<<dim3(2, n), 256, 0, s>>>(hb.keys, h->res_d, h->ctl, pass, hb.hc, hb.key_stride, pp.nlinesInSet); LAUNCH_CHECK();
+    k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(hb.accum, hb.keys, C, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
+    k_hough_topk<<<dim3(2, n), 256, 0, s>>>(hb.keys, h->res_d, C, pass, hb.hc, hb.key_stride, pp.nlinesInSet); LAUNCH_CHECK();
     if (flags & LFD_FULL_LINES) {
         if (!hb.lines) CK(cudaMalloc((void**)&hb.lines, (size_t)h->B * 2 * hb.line_stride * sizeof(float)));
-        k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, h->ctl, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
+        k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, C, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
     }
     CK(cudaEventRecord(h->ev[tbase + 6], s));
-    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, h->ctl, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh); LAUNCH_CHECK();
-    k_pass_end<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, n, pass, hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh); LAUNCH_CHECK();
+    k_pass_end<<<(n + 127) / 128, 128, 0, s>>>(C, n, pass, hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 7], s));
     return LFD_OK;
 }
@@ -623,7 +667,7 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     CK(cudaMemsetAsync(h->counters_d, 0, 16 * sizeof(int64_t), s));
     CK(cudaEventRecord(h->ev[0], s));
     if (h->ktiming) { h->kn = 0; ktime_mark(h, 0); }
-    k_ctl_init<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->res_d, n, mode != 2, mode != 1); LAUNCH_CHECK();
+    k_ctl_init<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode != 2, mode != 1); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->hist, 0, (size_t)2 * h->B * 256 * sizeof(u32), s));
     if (mode == 0) {
         CK(cudaMemsetAsync(h->starmask, 0, (size_t)n * d.NW * sizeof(u32), s));
@@ -654,12 +698,22 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     }
     CK(cudaEventRecord(h->ev[2], s));
     int rc;
-    if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags)) != LFD_OK) return rc; }
+    // The bright and the dim pass of a batch are independent until the verdict (the reference runs dim only
+    // when bright finds nothing, detecttrails.py:125-129; here dim runs for every frame on a second stream and
+    // k_finalize drops it where bright detected).  Most kernels after the morphology are latency-bound, so the
+    // two passes overlap almost completely.  LFD_SERIAL_PASSES keeps one stream (clean per-stage timings).
+    const bool overlap = mode == 0 && !(flags & LFD_SERIAL_PASSES) && !h->ktiming;
+    cudaStream_t s1 = overlap ? h->stream2 : s;
+    if (overlap) { CK(cudaEventRecord(h->ev_fork, s)); CK(cudaStreamWaitEvent(s1, h->ev_fork, 0)); }
+    if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags, s)) != LFD_OK) return rc; }
     else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
-    if (mode != 1) { if ((rc = run_pass_kernels(h, n, 1, flags)) != LFD_OK) return rc; }
+    if (mode != 1) { if ((rc = run_pass_kernels(h, n, 1, flags, s1)) != LFD_OK) return rc; }
     else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+    if (overlap) { CK(cudaEventRecord(h->ev_join, s1)); CK(cudaStreamWaitEvent(s, h->ev_join, 0)); }
+    k_finalize<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->ctl_h + h->B, h->ctl + h->B, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(h->ev[N_TIMINGS], s));
     h->last_n = n; h->last_flags = flags; h->pending = true;
@@ -779,7 +833,8 @@ extern "C" int lfd_get_stage_count(lfd_handle* h, int frame, int pass, int stage
     const HoughBufs& hb = h->hb[pass];
     switch (stage) {
     case LFD_STAGE_RECTS: {
-        *count = min(h->ctl_h[frame].ncomp_saved[pass][0], h->cfg.max_components) + min(h->ctl_h[frame].ncomp_saved[pass][1], h->cfg.max_components);
+        const FrameCtl& ch = h->ctl_h[(size_t)pass * h->B + frame];
+        *count = min(ch.ncomp_saved[pass][0], h->cfg.max_components) + min(ch.ncomp_saved[pass][1], h->cfg.max_components);
         return LFD_OK;
     }
     case LFD_STAGE_LINES_EQU: *count = h->res_h[frame].n_lines_equ[pass]; return LFD_OK;
@@ -829,11 +884,12 @@ extern "C" int lfd_get_stage(lfd_handle* h, int frame, int pass, int stage, void
     case LFD_STAGE_BG_LABELS: {
         if (!h->labels_tap) { int rc = dev_alloc(h, &h->labels_tap, N); if (rc) return rc; }
         int kind = stage == LFD_STAGE_BG_LABELS;
-        k_ccl_labels<<<(d.H + CCL_WARPS - 1) / CCL_WARPS, CCL_WARPS * 32, 0, s>>>(h->ccl_d[kind], h->labels_tap, h->ctl, pass, d, kind, frame); LAUNCH_CHECK();
+        k_ccl_labels<<<(d.H + CCL_WARPS - 1) / CCL_WARPS, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][kind], h->labels_tap, h->ctl + (size_t)pass * h->B, pass, d, kind, frame); LAUNCH_CHECK();
         src = h->labels_tap; need = N * sizeof(int); break;
     }
     case LFD_STAGE_RECTS: {
-        int n0 = min(h->ctl_h[frame].ncomp_saved[pass][0], h->cfg.max_components), n1 = min(h->ctl_h[frame].ncomp_saved[pass][1], h->cfg.max_components);
+        const FrameCtl& ch = h->ctl_h[(size_t)pass * h->B + frame];
+        int n0 = min(ch.ncomp_saved[pass][0], h->cfg.max_components), n1 = min(ch.ncomp_saved[pass][1], h->cfg.max_components);
         need = (size_t)(n0 + n1) * sizeof(lfd_rect);
         if (bytes < need) { h->err = "buffer too small"; return LFD_E_ARG; }
         const RectBuf& rb = h->rbuf_h[pass][frame];
@@ -901,7 +957,7 @@ extern "C" int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, in
         CK(cudaMalloc((void**)&hs.img, (size_t)d.N));
         CK(cudaMalloc((void**)&hs.mask, (size_t)d.NW * sizeof(u32)));
         CK(cudaMalloc((void**)&hs.segs, (size_t)2 * d.NW * sizeof(uint2)));
-        CK(cudaMalloc((void**)&hs.ctl, sizeof(FrameCtl)));
+        CK(cudaMalloc((void**)&hs.ctl, 2 * sizeof(FrameCtl)));
         CK(cudaMalloc((void**)&hs.res, sizeof(lfd_result)));
         hs.H = height; hs.W = width;
     }
@@ -909,7 +965,7 @@ extern "C" int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, in
     if (rc != LFD_OK) return rc;
     HoughBufs& hb = hs.hb;
     CK(cudaMemcpyAsync(hs.img, img, (size_t)d.N, cudaMemcpyHostToDevice, s));
-    k_ctl_init<<<1, 32, 0, s>>>(hs.ctl, hs.res, 1, 1, 0); LAUNCH_CHECK();
+    k_ctl_init<<<1, 32, 0, s>>>(hs.ctl, 1, hs.res, 1, 1, 0); LAUNCH_CHECK();
     // mark Hough as enabled for pass 0
     FrameCtl c; memset(&c, 0, sizeof(c)); c.active[0] = 1; c.hough[0] = 1;
     CK(cudaMemcpyAsync(hs.ctl, &c, sizeof(c), cudaMemcpyHostToDevice, s));
