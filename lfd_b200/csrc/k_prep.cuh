@@ -179,63 +179,144 @@ __device__ __forceinline__ void hist4(u32 g, u32& n0, u32& n1, u32& n2, u32* sh)
     }
 }
 
+// rint to u8 for 0 <= a < 256: a + 2^23 leaves round-half-even(a) in the low mantissa byte (FADD rounds to
+// nearest even) - one full-rate FP32 instruction instead of a quarter-rate F2I.  Anything that needs
+// saturation or special handling (a >= 255.5, |v| >= 2^31, inf - which cv2 maps to 0, not 255) shows up as a
+// non-zero bit in 0x00ffff00 of the sum's bit pattern and is redone exactly by the caller.
+__device__ __forceinline__ u32 rint_bits(float a) { return __float_as_uint(__fadd_rn(a, 8388608.0f)); }
+#define RINT_BITS_OVERFLOW 0x00ffff00u
+
+__device__ __forceinline__ u32 pack_low_bytes(u32 u0, u32 u1, u32 u2, u32 u3)
+{
+    return __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+}
+
+// histogram of four packed u8 values.  Sky-subtracted frames are almost entirely 0 (not counted at all: the zero
+// bin is the remainder) and 1 (one popc); anything else goes to shared-memory atomics.
+__device__ __forceinline__ void hist4_fast(u32 g, u32& n1, u32& nbig, u32* sh)
+{
+    n1 += __popc(g);                               // exact when every byte is 0 or 1 ...
+    if (g & 0xfefefefeu) {                         // ... otherwise (rare) take it back and count byte by byte
+        n1 -= __popc(g);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 c = (g >> (8 * k)) & 0xffu;
+            if (c == 1u) n1++;
+            else if (c >= 2u) { atomicAdd(&sh[c], 1u); nbig++; }
+        }
+    }
+}
+
+// one float4: mask, clips, both conversions.  t[] are the un-flipped-source pixels of 4 consecutive columns.
+template <int MODE>
+__device__ __forceinline__ void prep4(float4 v, u32 mb, int bigendian, float minFlux, float addFlux, u32& g0, u32& g1)
+{
+    if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+    if (MODE == 0 && mb) {
+        if (mb & 1u) v.x = 0.0f;
+        if (mb & 2u) v.y = 0.0f;
+        if (mb & 4u) v.z = 0.0f;
+        if (mb & 8u) v.w = 0.0f;
+    }
+    float t[4] = {v.x, v.y, v.z, v.w};
+    u32 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float tt = t[k];
+        if (MODE != 2) {
+            tt = fmaxf(tt, 0.0f);              // v < 0 -> 0 ; NaN -> 0 (the reference keeps NaN, which converts to 0 too)
+            a[k] = rint_bits(tt);
+        }
+        if (MODE != 1) {
+            float bb = (tt < minFlux) ? 0.0f : tt;
+            bb = (bb > 0.0f) ? __fadd_rn(bb, addFlux) : bb;
+            if (MODE == 2) bb = fabsf(bb);     // standalone dim: negative input -> |v| ; NaN fails the overflow test below
+            b[k] = rint_bits(bb);
+        }
+    }
+    g0 = (MODE != 2) ? pack_low_bytes(a[0], a[1], a[2], a[3]) : 0u;
+    g1 = (MODE != 1) ? pack_low_bytes(b[0], b[1], b[2], b[3]) : 0u;
+    // exact redo of the rare pixels that need saturation / special values
+    if ((a[0] | a[1] | a[2] | a[3] | b[0] | b[1] | b[2] | b[3]) & RINT_BITS_OVERFLOW) {
+        g0 = 0; g1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float tt = t[k];
+            if (MODE != 2) { tt = fmaxf(tt, 0.0f); g0 |= csa_fast(tt) << (8 * k); }
+            if (MODE != 1) {
+                float bb = (tt < minFlux) ? 0.0f : tt;
+                bb = (bb > 0.0f) ? __fadd_rn(bb, addFlux) : bb;
+                g1 |= csa_fast(bb) << (8 * k);
+            }
+        }
+    }
+}
+
 // MODE 0: pipeline (mask + flip, both passes) ; 1: bright only ; 2: dim only (no bright clip).
-// One CTA walks whole rows (no integer division); a thread converts 4 px per 16-byte load.
+// One CTA walks whole rows (no integer division); a thread converts 2 x 4 px per iteration, both 16-byte
+// loads issued before either is processed (bytes in flight per SM are what bounds a streaming kernel).
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0, u8* __restrict__ gray1,
        u32* __restrict__ hist0, u32* __restrict__ hist1, Dims d, int bigendian, float minFlux, float addFlux)
 {
+    // grid = (rows-CTAs per frame, frames), sized by the host to one wave of resident CTAs.  A CTA walks whole
+    // rows (no integer division), two rows per iteration: a thread issues four 16-byte loads before it converts
+    // anything - bytes in flight per SM, not instruction issue, bound this streaming kernel.
     __shared__ u32 sh[2][256];
     const int f = blockIdx.y;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const float* src = in + (size_t)f * d.N;
     const int wq = d.W >> 2;
-    u32 a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;     // popc sums (8 per matching byte)
-    for (int y = blockIdx.x; y < d.H; y += gridDim.x) {
-        const int sy = (MODE == 0) ? (d.H - 1 - y) : y;
-        const float4* srow = reinterpret_cast<const float4*>(src + (size_t)sy * d.W);
-        const u32* mrow = mask + (size_t)f * d.NW + (size_t)y * d.WW;
-        u32* o0 = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)y * d.W);
-        u32* o1 = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)y * d.W);
-        for (int xq = threadIdx.x; xq < wq; xq += blockDim.x) {
-            float4 v = __ldcs(srow + xq);
-            if (bigendian) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+    u32 a1 = 0, abig = 0, b1 = 0, bbig = 0, nwords = 0;
+    for (int ya = blockIdx.x; ya < d.H; ya += 2 * gridDim.x) {
+        const int yb = ya + gridDim.x;
+        const bool rowb = yb < d.H;
+        const int ybc = rowb ? yb : ya;
+        const int sya = (MODE == 0) ? (d.H - 1 - ya) : ya, syb = (MODE == 0) ? (d.H - 1 - ybc) : ybc;
+        const float4* srowa = reinterpret_cast<const float4*>(src + (size_t)sya * d.W);
+        const float4* srowb = reinterpret_cast<const float4*>(src + (size_t)syb * d.W);
+        const u32* mrowa = mask + (size_t)f * d.NW + (size_t)ya * d.WW;
+        const u32* mrowb = mask + (size_t)f * d.NW + (size_t)ybc * d.WW;
+        u32* o0a = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)ya * d.W);
+        u32* o1a = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)ya * d.W);
+        u32* o0b = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)ybc * d.W);
+        u32* o1b = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)ybc * d.W);
+        for (int xq = threadIdx.x; xq < wq; xq += 2 * blockDim.x) {
+            const int xq2 = xq + blockDim.x;
+            const bool two = xq2 < wq;
+            const int xq2c = two ? xq2 : xq;
+            float4 v[4];
+            v[0] = __ldcs(srowa + xq); v[1] = __ldcs(srowa + xq2c);
+            v[2] = __ldcs(srowb + xq); v[3] = __ldcs(srowb + xq2c);
+            u32 m[4] = {0, 0, 0, 0};
             if (MODE == 0) {
-                u32 mb = (mrow[xq >> 3] >> ((xq & 7) << 2)) & 0xfu;
-                if (mb) {
-                    if (mb & 1u) v.x = 0.0f;
-                    if (mb & 2u) v.y = 0.0f;
-                    if (mb & 4u) v.z = 0.0f;
-                    if (mb & 8u) v.w = 0.0f;
-                }
+                m[0] = (__ldg(mrowa + (xq >> 3)) >> ((xq & 7) << 2)) & 0xfu;
+                m[1] = (__ldg(mrowa + (xq2c >> 3)) >> ((xq2c & 7) << 2)) & 0xfu;
+                m[2] = (__ldg(mrowb + (xq >> 3)) >> ((xq & 7) << 2)) & 0xfu;
+                m[3] = (__ldg(mrowb + (xq2c >> 3)) >> ((xq2c & 7) << 2)) & 0xfu;
             }
-            float t[4] = {v.x, v.y, v.z, v.w};
-            u32 g0 = 0, g1 = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float tt = t[k];
-                if (MODE != 2) {
-                    tt = fmaxf(tt, 0.0f);          // v < 0 -> 0 ; NaN -> 0 (the reference keeps NaN, which converts to 0 too)
-                    g0 |= csa_fast(tt) << (8 * k);
-                }
-                if (MODE != 1) {
-                    float b = (tt < minFlux) ? 0.0f : tt;
-                    b = (b > 0.0f) ? __fadd_rn(b, addFlux) : b;
-                    g1 |= csa_fast(b) << (8 * k);
-                }
+                const bool on = (k == 0) || (k == 1 && two) || (k == 2 && rowb) || (k == 3 && two && rowb);
+                if (!on) continue;
+                u32 g0, g1;
+                prep4<MODE>(v[k], m[k], bigendian, minFlux, addFlux, g0, g1);
+                const int xo = (k & 1) ? xq2 : xq;
+                if (MODE != 2) { ((k & 2) ? o0b : o0a)[xo] = g0; hist4_fast(g0, a1, abig, sh[0]); }
+                if (MODE != 1) { ((k & 2) ? o1b : o1a)[xo] = g1; hist4_fast(g1, b1, bbig, sh[1]); }
+                nwords++;
             }
-            if (MODE != 2) { o0[xq] = g0; hist4(g0, a0, a1, a2, sh[0]); }
-            if (MODE != 1) { o1[xq] = g1; hist4(g1, b0, b1, b2, sh[1]); }
         }
     }
-    u32 acc[6] = {a0, a1, a2, b0, b1, b2};
+    // bins 1 and 0 from the register counters (0 = everything that was not counted elsewhere)
+    u32 acc[4] = {a1, 4u * nwords - a1 - abig, b1, 4u * nwords - b1 - bbig};
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 4; k++) {
         u32 vsum = acc[k];
         for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(FULLMASK, vsum, o);
-        if (lane_id() == 0 && vsum) atomicAdd(&sh[k / 3][k % 3], vsum >> 3);
+        if (lane_id() == 0 && vsum) atomicAdd(&sh[k >> 1][(k & 1) ? 0 : 1], vsum);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {

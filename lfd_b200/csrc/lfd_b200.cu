@@ -104,6 +104,7 @@ struct lfd_handle {
     cudaEvent_t ev[N_TIMINGS + 1];
     bool ev_valid[N_TIMINGS + 1];
     float timings[N_TIMINGS];
+    int prep_grid[3] = {0, 0, 0};     // resident CTAs of k_prep<mode> on this device (one full wave)
     cudaEvent_t mark[4];              // caller-placed timestamps on the handle's stream (lfd_timer_mark)
     bool mark_valid[4];
     // developer aid (env LFD_KTIMING=1): one event after every launch, reported by source line
@@ -385,6 +386,15 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        int per_sm[3] = {0, 0, 0};
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_prep<0>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_prep<1>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_prep<2>, 256, 0));
+        for (int m = 0; m < 3; m++) h->prep_grid[m] = prop.multiProcessorCount * (per_sm[m] > 0 ? per_sm[m] : 1);
+    }
     CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
     CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_smem(max_batch)));
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
@@ -688,12 +698,13 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
         k_prep_generic<<<dim3(pblocks, n), 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, clipped, d, mode, be,
                                                       (float)pd.minFlux, (float)pd.addFlux); LAUNCH_CHECK();
     } else {
-        // whole rows per CTA; 148 SMs x 8 CTAs of 256 threads, spread over the frames of the batch
-        int rb = (1184 + n - 1) / n; if (rb < 8) rb = 8; if (rb > d.H) rb = d.H;
+        // one wave of resident CTAs spread over the frames of the batch (a second, partial wave would double the time)
+        const float mf = (float)pd.minFlux, af = (float)pd.addFlux;
+        int rb = h->prep_grid[mode] / n; if (rb < 1) rb = 1; if (rb > d.H) rb = d.H;
         dim3 pg(rb, n);
-        if (mode == 0) k_prep<0><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
-        else if (mode == 1) k_prep<1><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
-        else k_prep<2><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, (float)pd.minFlux, (float)pd.addFlux);
+        if (mode == 0) k_prep<0><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
+        else if (mode == 1) k_prep<1><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
+        else k_prep<2><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
         LAUNCH_CHECK();
     }
     CK(cudaEventRecord(h->ev[2], s));
