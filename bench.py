@@ -449,9 +449,32 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # stdout carries exactly ONE line, the JSON: libraries that print to fd 1 while we run (NCCL's version banner,
+    # for one) are sent to stderr, and the real stdout is put back for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+    orig_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            orig_print(*a, **k)
+    builtins.print = capture
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":

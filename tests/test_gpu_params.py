@@ -96,3 +96,51 @@ def test_other_frame_shapes(cv2mod, shape):
         _check(h, 1, w1, pd, str(shape))
     finally:
         h.close()
+
+
+def test_special_float_values(cv2mod):
+    """NaN, +-inf, |v| >= 2^31, exact .5 ties and the 255 saturation edge go through convertScaleAbs the way cv2
+    does it: the fast conversion path must hand these to its exact slow path."""
+    from lfd_b200 import _lib
+    H, W = 96, 128
+    rng = np.random.default_rng(3)
+    img = rng.normal(0, 0.03, (H, W)).astype(np.float32)
+    specials = np.array([np.nan, np.inf, -np.inf, 2.0 ** 31, 2.0 ** 31 + 4096, 3.0e9, -3.0e9, 2147483520.0, 254.5, 255.0, 255.49, 255.5, 256.0,
+                         1000.0, 0.5, 1.5, 2.5, 3.5, 127.5, 128.5, -0.5, -1.5, 0.02, 0.019999, 1e-30, 65535.0, 16777216.0, 8388608.0, 8388607.5],
+                        np.float32)
+    ys = rng.integers(0, H, len(specials) * 3)
+    xs = rng.integers(0, W, len(specials) * 3)
+    img[ys, xs] = np.tile(specials, 3)
+    img[40:44, 10:110] += 30.0        # something for the later stages to find
+    pb, pd = dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM)
+    h = _lib.Handle(H, W, max_batch=2)
+    try:
+        h.set_params(pb, pd)
+        # standalone passes (run_pass, generic prep kernel with write-back)
+        for pass_, params in ((0, pb), (1, pd)):
+            work = img.copy()
+            if pass_ == 1:
+                with np.errstate(invalid="ignore"):
+                    work[work < 0] = 0
+            ref = work.copy()
+            taps = {}
+            with np.errstate(invalid="ignore"):
+                (rp.bright_pass if pass_ == 0 else rp.dim_pass)(ref, taps=taps, **params)
+            h.run_pass(pass_, work, flags=_lib.KEEP_TAPS, writeback=True)
+            assert np.array_equal(h.stage(0, pass_, "gray"), taps["gray"]), pass_
+            assert np.array_equal(work.view(np.uint32), ref.view(np.uint32)), pass_
+        # whole-frame path (fast prep kernel): the un-flipped frame goes in, gray comes out flipped
+        h.submit(np.stack([img, img]), [np.zeros((0, 4), np.int32)] * 2, flags=_lib.KEEP_TAPS | _lib.SERIAL_PASSES)
+        h.wait()
+        work = np.ascontiguousarray(img[::-1]).copy()
+        tb, td = {}, {}
+        with np.errstate(invalid="ignore"):
+            rp.bright_pass(work, taps=tb, **pb)
+            rp.dim_pass(work, taps=td, **pd)
+        for fr in (0, 1):
+            assert np.array_equal(h.stage(fr, 0, "gray"), tb["gray"])
+            assert np.array_equal(h.stage(fr, 1, "gray"), td["gray"])
+            assert np.array_equal(h.stage(fr, 0, "hist").astype(np.int64), np.bincount(tb["gray"].ravel(), minlength=256))
+            assert np.array_equal(h.stage(fr, 1, "hist").astype(np.int64), np.bincount(td["gray"].ravel(), minlength=256))
+    finally:
+        h.close()
