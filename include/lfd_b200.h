@@ -190,6 +190,10 @@ int lfd_hough_dims(int height, int width, double rho, double theta, int* numangl
 int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, double rho, double theta,
                     int threshold, float* lines, int max_lines, int* n_lines, int32_t* accum);
 
+/* cv2.Canny(img, low, high) (aperture 3, L2gradient=False) as called at processfield.py:236, on a host uint8 image
+ * of the handle's frame size; edges_out: uint8 height*width, 0 / 255.  (Config-5 microbenchmark and parity.) */
+int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, uint8_t* edges_out);
+
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
 const char* lfd_timing_name(int i);

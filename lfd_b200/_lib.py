@@ -114,6 +114,7 @@ def lib():
         L.lfd_hough_lines.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        L.lfd_canny.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -304,6 +305,15 @@ class Handle:
                                          accum.ctypes.data_as(ctypes.c_void_p) if want_accum else None))
         k = min(n.value, cap)
         return (lines[:k].reshape(k, 1, 2).copy() if k else None), accum
+
+    def canny(self, img, low, high):
+        """cv2.Canny(img, low, high) for a uint8 image of this handle's frame size."""
+        img = np.ascontiguousarray(img, np.uint8)
+        if img.shape != (self.H, self.W):
+            raise ValueError("image shape must be (%d, %d)" % (self.H, self.W))
+        out = np.empty((self.H, self.W), np.uint8)
+        self._ck(self._L.lfd_canny(self.h, img.ctypes.data_as(ctypes.c_void_p), int(low), int(high), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     def timings(self):
         ms = (ctypes.c_float * 32)()

@@ -1003,6 +1003,50 @@ extern "C" int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// standalone cv2.Canny (aperture 3, L1 gradient) on a host uint8 image of the handle's frame size
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, uint8_t* edges_out)
+{
+    if (!h || !img || !edges_out || low < 0 || high < low) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    const Dims d = h->d;
+    cudaStream_t s = h->stream;
+    const int pass = 0, n = 1;
+    FrameCtl* const C = h->ctl;
+    CK(cudaMemcpyAsync(h->morph[pass], img, (size_t)d.N, cudaMemcpyHostToDevice, s));
+    k_ctl_init<<<1, 32, 0, s>>>(h->ctl, h->B, h->res_d, 1, 1, 0); LAUNCH_CHECK();
+    k_pass_begin<<<1, 32, 0, s>>>(C, 1); LAUNCH_CHECK();
+    k_pack_mask<<<592, 256, 0, s>>>(h->morph[pass], h->nz[pass], d); LAUNCH_CHECK();
+    if ((d.W % 8) == 0) {
+        const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
+        const int nunits = nstrips * nchunks;
+        k_nms_march<false><<<dim3((nunits + 3) / 4, n), 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d,
+                                                                  nstrips, nunits, low, high);
+    } else {
+        dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
+        k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d, low, high);
+    }
+    LAUNCH_CHECK();
+    dim3 rows((d.H + CCL_WARPS - 1) / CCL_WARPS, n);
+    const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
+    dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][0], C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], C, pass, d); LAUNCH_CHECK();
+    k_expand_mask<<<dim3(592, 1), 256, 0, s>>>(h->edges[pass], h->tap_u8, d); LAUNCH_CHECK();
+    FrameCtl out;
+    CK(cudaMemcpyAsync(&out, C, sizeof(out), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(edges_out, h->tap_u8, (size_t)d.N, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out.status & LFD_FRAME_OVERFLOW) { h->err = "edge map has more runs than lfd_config.max_runs"; return LFD_E_CAPACITY; }
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------------
 extern "C" int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries)

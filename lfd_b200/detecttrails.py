@@ -51,6 +51,12 @@ def default_params():
     return params_bright, params_dim, params_removestars
 
 
+# Opt-in: write the seven header values instead of the reference's literal "{h['CRPIX2']}" ...
+# placeholders, so that lfd.results.utils.parse_result_row (results/utils.py:185-210) can ingest the file.
+# Default False = byte-identical to the reference.
+FORMAT_HEADER_VALUES = False
+
+
 def _load_frame(run, camcol, filter, field):
     """detecttrails.py:73-117: resolve the path, unpack .bz2 if needed, read image + header.
     Returns (img, header_prefix_of_the_results_line)."""
@@ -82,6 +88,10 @@ def _load_frame(run, camcol, filter, field):
         printit = (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
                    "{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
                    "{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
+        if FORMAT_HEADER_VALUES:
+            printit = (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
+                       f"{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
+                       f"{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
         return img, printit
     finally:
         if removefits:
@@ -183,8 +193,25 @@ def write_records(results, errors, records):
             errors.write(text)
 
 
+def _progress_key(frame):
+    run, camcol, filter, field = frame
+    return f"{run} {camcol} {filter} {field}"
+
+
+def read_progress(path):
+    """Frames already finished by an earlier, interrupted run (one "run camcol filter field status" line each)."""
+    done = set()
+    if path and os.path.exists(path):
+        with open(path) as f:
+            for line in f:
+                t = line.split()
+                if len(t) >= 5:
+                    done.add(" ".join(t[:4]))
+    return done
+
+
 def process_fields(results, errors, frames, params_bright, params_dim, params_removestars, batch=16, device=0,
-                   distributed=None, compute=None):
+                   distributed=None, compute=None, progress=None):
     """Process an ordered list of (run, camcol, filter, field); results/errors are written in list order,
     exactly the lines the reference's per-frame loop would write.
 
@@ -197,12 +224,24 @@ def process_fields(results, errors, frames, params_bright, params_dim, params_re
     frames = list(frames)
     if distributed is None:
         distributed = sharding.is_distributed()
-    if not distributed:
-        write_records(results, errors, compute(frames))
-        return
-    merged = sharding.run_sharded(frames, compute, block=batch)
-    if merged is not None:          # rank 0
-        write_records(results, errors, merged)
+    # resumable runs: `progress` is a text file with one line per finished frame; frames listed
+    # there are skipped, and the file is extended chunk by chunk, after the chunk's results/errors lines are flushed
+    if progress:
+        done = read_progress(progress)
+        frames = [fr for fr in frames if _progress_key(fr) not in done]
+    writer = (not distributed) or sharding.rank() == 0
+    chunk = max(batch, 1) * (sharding.world_size() if distributed else 1) * 8
+    for i0 in range(0, len(frames), chunk):
+        part = frames[i0:i0 + chunk]
+        recs = sharding.run_sharded(part, compute, block=batch) if distributed else compute(part)
+        if not writer:
+            continue
+        write_records(results, errors, recs)
+        if progress:
+            results.flush(); errors.flush()
+            with open(progress, "a") as pf:
+                for fr, (kind, _text) in zip(part, recs):
+                    pf.write(_progress_key(fr) + " " + kind + "\n")
 
 
 def process_field(results, errors, run, camcol, filter, field, params_bright, params_dim, params_removestars):
@@ -214,15 +253,20 @@ def process_field(results, errors, run, camcol, filter, field, params_bright, pa
 class DetectTrails:
     """Convenience class that processes targeted SDSS frames (detecttrails.py:146-407).
 
-    Extra, optional kwargs that the reference does not have: ``batch`` (frames per GPU batch,
-    default 16) and ``device`` (CUDA device index, default 0)."""
+    Extra, optional kwargs that the reference does not have: ``batch`` (frames per GPU batch, default 16),
+    ``device`` (CUDA device index, default: LOCAL_RANK under torchrun, else 0) and ``resume`` (path of a progress
+    file, or True for ``<savepath>/progress.txt``: frames listed there are skipped and finished frames are appended,
+    so an interrupted run can be restarted without duplicating lines - the reference only appends, detecttrails.py:349).
+    Under torchrun (torch.distributed initialised) the frame list is sharded over the ranks and rank 0 writes."""
 
     def __init__(self, **kwargs):
         savepth = (kwargs["savepath"] if "savepath" in kwargs else ".")
         self.kwargs = kwargs
         self.params_bright, self.params_dim, self.params_removestars = default_params()
         self.batch = int(kwargs.get("batch", 16))
-        self.device = int(kwargs.get("device", 0))
+        self.device = int(kwargs.get("device", os.environ.get("LOCAL_RANK", 0)))
+        resume = kwargs.get("resume", None)
+        self.progress = (os.path.join(savepth, "progress.txt") if resume is True else resume) or None
 
         if "results" in kwargs:
             self.results = kwargs["results"]
@@ -335,4 +379,4 @@ class DetectTrails:
         """Run the selected frames; results/errors files are opened in append mode like the original."""
         with open(self.results, "a") as results, open(self.errors, "a") as errors:
             process_fields(results, errors, self.frame_list(), self.params_bright, self.params_dim,
-                           self.params_removestars, batch=self.batch, device=self.device)
+                           self.params_removestars, batch=self.batch, device=self.device, progress=self.progress)

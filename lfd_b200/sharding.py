@@ -16,6 +16,16 @@ def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def rank():
+    import torch.distributed as dist
+    return dist.get_rank() if is_distributed() else 0
+
+
+def world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if is_distributed() else 1
+
+
 def shard_indices(n, rank, world, block):
     """Indices of the frames rank `rank` processes: blocks of `block` consecutive frames, round-robin over ranks
     (full GPU batches, and neighbouring fields - which share catalog/FITS directories - stay together)."""

@@ -144,3 +144,37 @@ def test_special_float_values(cv2mod):
             assert np.array_equal(h.stage(fr, 1, "hist").astype(np.int64), np.bincount(td["gray"].ravel(), minlength=256))
     finally:
         h.close()
+
+
+def test_config5_microbench_hough_canny(cv2mod):
+    """BASELINE.json config 5: 4096x4096 frames, non-zero density sweep, rho / theta sweep, against cv2 directly
+    (bit-exact line lists and edge maps)."""
+    from lfd_b200 import _lib
+    S = 4096
+    rng = np.random.default_rng(55)
+    h = _lib.Handle(S, S, max_batch=1, max_runs=1 << 22)
+    try:
+        pb, pd = dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM)
+        h.set_params(pb, pd)
+        for density, rho, theta in ((0.001, 20, np.pi / 180), (0.01, 5, np.pi / 360), (0.03, 20, np.pi / 720), (0.10, 20, np.pi / 180),
+                                    (0.003, 1, np.pi / 180)):
+            img = (rng.random((S, S)) < density).astype(np.uint8) * 255
+            cv2mod.line(img, (100, 50), (3900, 3000), 255, 2)
+            cv2mod.line(img, (4000, 10), (30, 4090), 255, 1)
+            ref = cv2mod.HoughLines(img, rho, theta, 1)
+            got, _ = h.hough_lines(img, rho, theta, 1)
+            assert (ref is None) == (got is None)
+            assert got.shape == ref.shape, (density, rho, theta, got.shape, ref.shape)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (density, rho, theta)
+        # Canny on grey images of increasing busyness
+        for sigma, lo, hi in ((2.0, 0, 255), (6.0, 0, 255), (12.0, 50, 150)):
+            base = np.zeros((S, S), np.float32)
+            for _ in range(400):
+                y, x = rng.integers(50, S - 50, 2)
+                base[y - 6:y + 6, x - 6:x + 6] += rng.uniform(20, 200)
+            noisy = np.clip(base + rng.normal(0, sigma, (S, S)), 0, 255).astype(np.uint8)
+            ref = cv2mod.Canny(noisy, lo, hi)
+            got = h.canny(noisy, lo, hi)
+            assert np.array_equal(got, ref), (sigma, lo, hi, int((got != ref).sum()))
+    finally:
+        h.close()

@@ -93,6 +93,25 @@ def test_detecttrails_dropin(tmp_path, cv2mod):
     assert got == exp.getvalue()
     assert got.count("\n") >= 2
     assert (out / "errors.txt").read_text() == ""
+    # opt-in N2 format: the seven header values are written out, and the row parses as 17 columns of numbers
+    import lfd_b200.detecttrails as dtmod
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    dtmod.FORMAT_HEADER_VALUES = True
+    try:
+        lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", savepath=str(out2), batch=4, resume=True).process()
+    finally:
+        dtmod.FORMAT_HEADER_VALUES = False
+    rows = (out2 / "results.txt").read_text().splitlines()
+    assert len(rows) == got.count("\n")
+    for row, ref_row in zip(rows, got.splitlines()):
+        t = row.split()
+        assert len(t) == 17 and t[:6] == ref_row.split()[:6] and t[13:] == ref_row.split()[-4:]
+        [float(x) for x in t[4:]]
+    assert len((out2 / "progress.txt").read_text().splitlines()) == 4
+    # a second run with the same progress file has nothing left to do
+    lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", savepath=str(out2), batch=4, resume=True).process()
+    assert (out2 / "results.txt").read_text().splitlines() == rows
     # missing frame -> errors.txt, processing continues (detecttrails.py:84-87, :133-139)
     dt2 = lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", field=999, savepath=str(out))
     dt2.process()

@@ -73,3 +73,40 @@ def test_gloo_world2_ordered_gather(tmp_path):
     exp = "".join(t for k, t in recs if k == "line") + "---\n" + "".join(t for k, t in recs if k == "err")
     assert (tmp_path / "out0.txt").read_text() == exp          # rank 0 wrote everything, in sequential order
     assert (tmp_path / "out1.txt").read_text() == "---\n"      # other ranks write nothing
+
+
+def test_resume_skips_finished_frames(tmp_path):
+    """N3: an interrupted run restarted with the same progress file processes only what is left and appends nothing twice."""
+    from lfd_b200.detecttrails import process_fields, read_progress
+    frames = [(2888, 1, "r", f) for f in range(100, 160)]
+    calls = []
+
+    def compute(fr):
+        calls.append(list(fr))
+        return _fake_compute(fr)
+
+    class Boom(Exception):
+        pass
+
+    def compute_crashing(fr):
+        if any(f[3] >= 140 for f in fr):
+            raise Boom()
+        return compute(fr)
+
+    prog = str(tmp_path / "progress.txt")
+    res_p, err_p = tmp_path / "results.txt", tmp_path / "errors.txt"
+    with open(res_p, "a") as res, open(err_p, "a") as err:
+        with pytest.raises(Boom):
+            process_fields(res, err, frames, {"debug": False}, {"debug": False}, {}, batch=1, compute=compute_crashing,
+                           distributed=False, progress=prog)
+    done = read_progress(prog)
+    assert 0 < len(done) < len(frames)
+    with open(res_p, "a") as res, open(err_p, "a") as err:
+        process_fields(res, err, frames, {"debug": False}, {"debug": False}, {}, batch=1, compute=compute,
+                       distributed=False, progress=prog)
+    recs = _fake_compute(frames)
+    assert res_p.read_text() == "".join(t for k, t in recs if k == "line")
+    assert err_p.read_text() == "".join(t for k, t in recs if k == "err")
+    seen = [f for c in calls for f in c]
+    assert sorted(seen) == sorted(frames) and len(seen) == len(set(seen))      # every frame computed exactly once
+    assert len(read_progress(prog)) == len(frames)
