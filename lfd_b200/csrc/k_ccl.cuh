@@ -540,6 +540,55 @@ k_ccl_alloc(CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps, FrameCtl* __
     }
 }
 
+// 6+7 fused for the foreground pass (same grid, same runs): write the Canny edge mask of the row and allocate
+// the contours whose root run lies on it.
+__global__ void __launch_bounds__(CCL_WARPS * 32)
+k_ccl_edges_alloc(CclBuf* __restrict__ bufs, u32* __restrict__ edges, CompBuf* __restrict__ comps, FrameCtl* __restrict__ ctl,
+                  int pass, Dims d)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    int wid = threadIdx.x >> 5;
+    int y = blockIdx.x * CCL_WARPS + wid;
+    __shared__ u32 row[CCL_WARPS][128];
+    if (y >= d.H) return;
+    CclBuf b = bufs[f];
+    CompBuf cb = comps[f];
+    for (int w = lane_id(); w < d.WW; w += 32) row[wid][w] = 0;
+    __syncwarp();
+    if (ctl[f].nruns[0] > 0) {
+        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
+        for (int id = r0 + lane_id(); id < r1; id += 32) {
+            int root = b.parent[id];
+            if (!(b.flag[root] & 1)) continue;
+            Run r = b.runs[id];
+            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                atomicOr(&row[wid][w], bit_range(blo, bhi));
+            }
+            if (root != id) continue;
+            // this run is the raster-first run of an edge component: allocate its contour
+            int ci = atomicAdd(&ctl[f].ncomp[0], 1);
+            int hh = b.ymax[id] - y + 1;
+            int slot = atomicAdd(&ctl[f].nslots[0], hh);
+            int ho = atomicAdd(&ctl[f].nhull[0], 2 * hh + 2);
+            if (ci >= cb.maxcomp || slot + hh > cb.slotcap || ho + 2 * hh + 2 > cb.hullcap) {
+                atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
+                continue;
+            }
+            cb.root[ci] = id;
+            cb.y0[ci] = y;
+            cb.h[ci] = hh;
+            cb.slot[ci] = slot;
+            cb.hulloff[ci] = ho;
+            for (int i = 0; i < hh; i++) { cb.rowmin[slot + i] = 0x7fffffff; cb.rowmax[slot + i] = -1; }
+            b.compidx[id] = ci;
+        }
+    }
+    __syncwarp();
+    for (int w = lane_id(); w < d.WW; w += 32) edges[(size_t)f * d.NW + (size_t)y * d.WW + w] = row[wid][w];
+}
+
 // 8. per-row extremes of every contour's point set
 __global__ void __launch_bounds__(CCL_WARPS * 32)
 k_ccl_extremes(const u32* __restrict__ edges, CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps,

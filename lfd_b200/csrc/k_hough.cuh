@@ -251,7 +251,8 @@ k_hough_sort(u64* __restrict__ keys, float* __restrict__ lines, const FrameCtl* 
 // float64 arithmetic on float32-valued inputs like the NumPy original; a short second set leaves
 // theta1[i] at 0 as well (the four assignments share one try block, :93-102).
 __global__ void k_check_theta(lfd_result* __restrict__ res, FrameCtl* __restrict__ ctl, int pass, int n,
-                              int navg, double dro, double thetaTresh, double lineSetTresh)
+                              int navg, double dro, double thetaTresh, double lineSetTresh, int numangle,
+                              unsigned long long* __restrict__ counters)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
@@ -295,4 +296,16 @@ __global__ void k_check_theta(lfd_result* __restrict__ res, FrameCtl* __restrict
     // the frame's verdict (which pass counts, rho/theta, status) is assembled by k_finalize: the two passes run
     // concurrently and only write their own fields
     ctl[f].detected = detected ? 1 : 0;
+    // end-of-pass bookkeeping: contour counts for the RECTS tap, work counters of the batch
+    FrameCtl* c = ctl + f;
+    c->ncomp_saved[pass][0] = c->ncomp[0]; c->ncomp_saved[pass][1] = c->ncomp[1];
+    atomicAdd(&counters[0], (unsigned long long)c->nnz[0]);
+    atomicAdd(&counters[1], (unsigned long long)c->nnz[1]);
+    atomicAdd(&counters[2], (unsigned long long)(c->nnz[0] + c->nnz[1]) * numangle);
+    atomicAdd(&counters[3], (unsigned long long)c->nruns[0]);
+    atomicAdd(&counters[4], (unsigned long long)c->nruns[1]);
+    atomicAdd(&counters[5], (unsigned long long)(c->ncomp[0] + c->ncomp[1]));
+    atomicAdd(&counters[6], (unsigned long long)c->npass);
+    if (c->hough[pass]) atomicAdd(&counters[8], 1ull);
+    atomicAdd(&counters[9 + pass], 1ull);
 }

@@ -176,34 +176,6 @@ __global__ void k_ctl_init(FrameCtl* ctl, int B, lfd_result* res, int n, int act
     res[f] = r;
 }
 
-__global__ void k_pass_begin(FrameCtl* ctl, int n)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n) return;
-    FrameCtl* c = ctl + f;
-    c->nruns[0] = c->nruns[1] = 0; c->ncomp[0] = c->ncomp[1] = 0;
-    c->nslots[0] = c->nslots[1] = 0; c->nhull[0] = c->nhull[1] = 0;
-    c->npass = 0; c->nseg[0] = c->nseg[1] = 0; c->npeaks[0] = c->npeaks[1] = 0; c->nnz[0] = c->nnz[1] = 0;
-}
-
-__global__ void k_pass_end(FrameCtl* ctl, int n, int pass, int numangle, unsigned long long* counters)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n) return;
-    FrameCtl* c = ctl + f;
-    if (!c->active[pass]) return;
-    c->ncomp_saved[pass][0] = c->ncomp[0]; c->ncomp_saved[pass][1] = c->ncomp[1];
-    atomicAdd(&counters[0], (unsigned long long)c->nnz[0]);
-    atomicAdd(&counters[1], (unsigned long long)c->nnz[1]);
-    atomicAdd(&counters[2], (unsigned long long)(c->nnz[0] + c->nnz[1]) * numangle);
-    atomicAdd(&counters[3], (unsigned long long)c->nruns[0]);
-    atomicAdd(&counters[4], (unsigned long long)c->nruns[1]);
-    atomicAdd(&counters[5], (unsigned long long)(c->ncomp[0] + c->ncomp[1]));
-    atomicAdd(&counters[6], (unsigned long long)c->npass);
-    if (c->hough[pass]) atomicAdd(&counters[8], 1ull);
-    atomicAdd(&counters[9 + pass], 1ull);
-}
-
 // Verdict of the frame from the two passes' private results (detecttrails.py:125-131): bright wins; the dim
 // pass counts only where bright neither detected nor failed, and is reported as "not run" elsewhere.
 // mode 0: both passes ; 1: bright only ; 2: dim only
@@ -571,7 +543,6 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
-    k_pass_begin<<<(n + 127) / 128, 128, 0, s>>>(C, n); LAUNCH_CHECK();
     // LUT + morphology
     k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist, h->lut, C, h->B, d.N, pass); LAUNCH_CHECK();
     MorphCfg mc;
@@ -630,8 +601,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], C, pass, d); LAUNCH_CHECK();
-    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_edges_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], h->comp_d[pass], C, pass, d); LAUNCH_CHECK();
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 3], s));
     // background runs: hole contours
@@ -662,8 +632,8 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
         k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, C, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
     }
     CK(cudaEventRecord(h->ev[tbase + 6], s));
-    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh); LAUNCH_CHECK();
-    k_pass_end<<<(n + 127) / 128, 128, 0, s>>>(C, n, pass, hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh,
+                                              hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev[tbase + 7], s));
     return LFD_OK;
 }
@@ -1016,7 +986,6 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     FrameCtl* const C = h->ctl;
     CK(cudaMemcpyAsync(h->morph[pass], img, (size_t)d.N, cudaMemcpyHostToDevice, s));
     k_ctl_init<<<1, 32, 0, s>>>(h->ctl, h->B, h->res_d, 1, 1, 0); LAUNCH_CHECK();
-    k_pass_begin<<<1, 32, 0, s>>>(C, 1); LAUNCH_CHECK();
     k_pack_mask<<<592, 256, 0, s>>>(h->morph[pass], h->nz[pass], d); LAUNCH_CHECK();
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
