@@ -104,6 +104,13 @@ struct lfd_handle {
     cudaEvent_t ev[N_TIMINGS + 1];
     bool ev_valid[N_TIMINGS + 1];
     float timings[N_TIMINGS];
+    // CUDA graph of the two passes + verdict + result copies (whole-frame path without taps): ~100 small launches
+    // become one graph launch, which removes the per-launch gaps between the latency-bound kernels
+    bool use_graphs = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_n = 0, graph_flags = 0;
+    int64_t graph_launches = 0;
+    bool stage_timings_valid = true;
     int prep_grid[3] = {0, 0, 0};     // resident CTAs of k_prep<mode> on this device (one full wave)
     cudaEvent_t mark[4];              // caller-placed timestamps on the handle's stream (lfd_timer_mark)
     bool mark_valid[4];
@@ -325,6 +332,7 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->counters_h) cudaFreeHost(h->counters_h);
     for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; i++) if (h->mark_valid[i]) cudaEventDestroy(h->mark[i]);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -341,6 +349,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     CK(cudaSetDevice(device));
     h->device = device;
     { const char* kt = getenv("LFD_KTIMING"); h->ktiming = kt && kt[0] == '1'; }
+    { const char* ng = getenv("LFD_NO_GRAPH"); h->use_graphs = !(ng && ng[0] == '1'); }
     if (max_batch < 1 || H < 8 || W < 8) { h->err = "bad batch or frame size"; return LFD_E_ARG; }
     if (W % 4 != 0) { h->err = "frame width must be a multiple of 4"; return LFD_E_UNSUPPORTED; }
     if (W > 4096 || H > 65535) { h->err = "frame too large (W <= 4096, H <= 65535)"; return LFD_E_UNSUPPORTED; }
@@ -525,14 +534,16 @@ extern "C" int lfd_set_params(lfd_handle* h, const lfd_params* p)
     }
     h->params = *p;
     h->have_params = true;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // kernel arguments changed
     return LFD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the pipeline
 // ------------------------------------------------------------------------------------------------
-static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStream_t s)
+static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStream_t s, bool stage_events)
 {
+#define STAGE_EVENT(i) do { if (stage_events) CK(cudaEventRecord(h->ev[i], s)); } while (0)
     const Dims d = h->d;
     const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
     FrameCtl* const C = h->ctl + (size_t)pass * h->B;      // this pass's bookkeeping block
@@ -576,7 +587,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
         }
         LAUNCH_CHECK();
     }
-    CK(cudaEventRecord(h->ev[tbase + 1], s));
+    STAGE_EVENT(tbase + 1);
     // Sobel + NMS
     u8* ntap = nullptr;
     if (taps) {
@@ -594,7 +605,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
         k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, 0, 255);
     }
     LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[tbase + 2], s));
+    STAGE_EVENT(tbase + 2);
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][0], C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
@@ -603,7 +614,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_edges_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], h->comp_d[pass], C, pass, d); LAUNCH_CHECK();
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[tbase + 3], s));
+    STAGE_EVENT(tbase + 3);
     // background runs: hole contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][1], C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
@@ -612,12 +623,12 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[tbase + 4], s));
+    STAGE_EVENT(tbase + 4);
     // rectangles + box image
     k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d[pass], h->rbuf_d[pass], h->ccl_d[pass][0], h->ccl_d[pass][1], C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], C, pass, d); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[tbase + 5], s));
+    STAGE_EVENT(tbase + 5);
     // Hough on the morphology output and on the box image
     CK(cudaMemsetAsync(hb.accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
     k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs[pass], C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
@@ -631,11 +642,12 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
         if (!hb.lines) CK(cudaMalloc((void**)&hb.lines, (size_t)h->B * 2 * hb.line_stride * sizeof(float)));
         k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, C, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
     }
-    CK(cudaEventRecord(h->ev[tbase + 6], s));
+    STAGE_EVENT(tbase + 6);
     k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh,
                                               hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
-    CK(cudaEventRecord(h->ev[tbase + 7], s));
+    STAGE_EVENT(tbase + 7);
     return LFD_OK;
+#undef STAGE_EVENT
 }
 
 // mode 0: whole-frame pipeline on h->in (un-flipped) ; mode 1/2: standalone bright/dim on frame slot 0
@@ -684,18 +696,47 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     // k_finalize drops it where bright detected).  Most kernels after the morphology are latency-bound, so the
     // two passes overlap almost completely.  LFD_SERIAL_PASSES keeps one stream (clean per-stage timings).
     const bool overlap = mode == 0 && !(flags & LFD_SERIAL_PASSES) && !h->ktiming;
+    const bool graph = overlap && h->use_graphs && !(flags & (LFD_KEEP_TAPS | LFD_FULL_LINES));
     cudaStream_t s1 = overlap ? h->stream2 : s;
-    if (overlap) { CK(cudaEventRecord(h->ev_fork, s)); CK(cudaStreamWaitEvent(s1, h->ev_fork, 0)); }
-    if (mode != 2) { if ((rc = run_pass_kernels(h, n, 0, flags, s)) != LFD_OK) return rc; }
-    else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
-    if (mode != 1) { if ((rc = run_pass_kernels(h, n, 1, flags, s1)) != LFD_OK) return rc; }
-    else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
-    if (overlap) { CK(cudaEventRecord(h->ev_join, s1)); CK(cudaStreamWaitEvent(s, h->ev_join, 0)); }
-    k_finalize<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->ctl_h + h->B, h->ctl + h->B, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    h->stage_timings_valid = !graph;
+    // everything from the fork to the result copies; captured into a CUDA graph when `graph`
+    auto passes = [&](bool stage_events) -> int {
+        int rc2;
+        if (overlap) { CK(cudaEventRecord(h->ev_fork, s)); CK(cudaStreamWaitEvent(s1, h->ev_fork, 0)); }
+        if (mode != 2) { if ((rc2 = run_pass_kernels(h, n, 0, flags, s, stage_events)) != LFD_OK) return rc2; }
+        else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
+        if (mode != 1) { if ((rc2 = run_pass_kernels(h, n, 1, flags, s1, stage_events)) != LFD_OK) return rc2; }
+        else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+        if (overlap) { CK(cudaEventRecord(h->ev_join, s1)); CK(cudaStreamWaitEvent(s, h->ev_join, 0)); }
+        k_finalize<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->ctl_h + h->B, h->ctl + h->B, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        return LFD_OK;
+    };
+    if (graph) {
+        if (!h->graph_exec || h->graph_n != n || h->graph_flags != flags) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            const int64_t l0 = h->launches;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = passes(false);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != LFD_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+            if (ce != cudaSuccess) { h->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return LFD_E_CUDA; }
+            ce = cudaGraphInstantiate(&h->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { h->graph_exec = nullptr; h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return LFD_E_CUDA; }
+            h->graph_launches = h->launches - l0;
+            h->launches = l0;
+            h->graph_n = n; h->graph_flags = flags;
+        }
+        CK(cudaGraphLaunch(h->graph_exec, s));
+        h->launches += h->graph_launches;
+    } else {
+        if ((rc = passes(true)) != LFD_OK) return rc;
+    }
     CK(cudaEventRecord(h->ev[N_TIMINGS], s));
     h->last_n = n; h->last_flags = flags; h->pending = true;
     return LFD_OK;
@@ -756,7 +797,9 @@ extern "C" int lfd_wait(lfd_handle* h, lfd_result* out)
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < N_TIMINGS; i++) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+        // in graph mode only the setup and k_prep brackets (recorded outside the graph) exist
+        if (h->stage_timings_valid || i < 2)
+            if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
         h->timings[i] = ms;
     }
     if (out) memcpy(out, h->res_h, (size_t)h->last_n * sizeof(lfd_result));
