@@ -217,6 +217,42 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def dropin_leg(device, ndistinct=32, nfields=256, batch=32):
+    """Frames/s of the user-facing call: a synthetic SDSS tree on local disk (FITS frames + photoObj tables),
+    lfd_b200.DetectTrails(run=, camcol=, filter=).process() writing results.txt - FITS reads (page cache), catalog
+    filtering, pinned staging, H2D, kernels, D2H and the text output all inside the timed region.  `ndistinct`
+    synthetic fields are generated and hard-linked up to `nfields` file names (generation time, not run time)."""
+    import shutil
+    import lfd_b200
+    root = tempfile.mkdtemp(prefix="lfd_b200_bench_")
+    try:
+        tree = synth.write_sdss_tree(root, 2888, 1, range(100, 100 + ndistinct), filters=("r",), startfield=100, endfield=100 + nfields)
+        fdir = os.path.join(tree["photoobjpath"], "frames", "301", "2888", "1")
+        odir = os.path.join(tree["photoobjpath"], "301", "2888", "1")
+        for k in range(ndistinct, nfields):
+            src = 100 + k % ndistinct
+            os.link(os.path.join(fdir, "frame-r-002888-1-%04d.fits" % src), os.path.join(fdir, "frame-r-002888-1-%04d.fits" % (100 + k)))
+            os.link(os.path.join(odir, "photoObj-002888-1-%04d.fits" % src), os.path.join(odir, "photoObj-002888-1-%04d.fits" % (100 + k)))
+        lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], root)
+        best = None
+        for rep_i in range(3):                       # first repetition warms the page cache and creates the handles
+            out = os.path.join(root, "out%d" % rep_i)
+            os.makedirs(out)
+            dt = lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", savepath=out, batch=batch, device=device)
+            t0 = time.perf_counter()
+            dt.process()
+            el = time.perf_counter() - t0
+            if rep_i > 0:
+                best = el if best is None else min(best, el)
+        nlines = sum(1 for _ in open(os.path.join(out, "results.txt")))
+        return {"value": nfields / best, "unit": "frames/s", "frames": nfields, "batch": batch, "detections": nlines,
+                "how": "DetectTrails(run, camcol, filter).process() on a synthetic tree in %s (%d distinct fields hard-linked to %d): "
+                       "raw FITS payload read into pinned staging by loader threads (page cache), photoObj filtering, ring of three "
+                       "handles, results.txt written; best of 2 after a warm-up pass" % (tempfile.gettempdir(), ndistinct, nfields)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -407,6 +443,14 @@ def run_ours(args):
                         "sample": "%d frames of the same pool, oracle/ref_pipeline.py (reference call sequence on cv2 %s), "
                                   "multiprocessing.Pool(%d), cv2.setNumThreads(1), %.1f s" % (sample, cv2.__version__, cores, cpu_s)}
 
+    # ---- the drop-in itself: FITS files on disk -> DetectTrails(...).process() -> results.txt (N=1 only) --------
+    dropin = None
+    if world == 1 and not args.no_dropin:
+        try:
+            dropin = dropin_leg(local)
+        except Exception as e:   # noqa: BLE001 - an extra, never fatal for the contract line
+            dropin = {"error": "%s: %s" % (type(e).__name__, e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -431,6 +475,7 @@ def run_ours(args):
                   "frames_hough": counters["frames_hough"]},
         "counters": counters,
         "cpu_baseline": cpu_baseline,
+        "dropin_e2e": dropin,
     }
     print(json.dumps(line))
     if distributed:
@@ -446,6 +491,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (target command for ncu)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the DetectTrails-on-FITS-files leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

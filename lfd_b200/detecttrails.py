@@ -57,9 +57,10 @@ def default_params():
 FORMAT_HEADER_VALUES = False
 
 
-def _load_frame(run, camcol, filter, field):
+def _load_frame(run, camcol, filter, field, raw=False):
     """detecttrails.py:73-117: resolve the path, unpack .bz2 if needed, read image + header.
-    Returns (img, header_prefix_of_the_results_line)."""
+    Returns (img, header_prefix_of_the_results_line[, big_endian]).  With raw=True and the built-in FITS reader the
+    image is the undecoded big-endian payload (uint32 view) and big_endian is True: the device byte-swaps."""
     removefits = False
     fitspath = None
     try:
@@ -82,34 +83,24 @@ def _load_frame(run, camcol, filter, field):
             removefits = True
         else:
             fitspath = origfitspath
-        img = fitsio.read(fitspath)
-        h = fitsio.read_header(fitspath)
-        # only the first fragment is an f-string in the reference (detecttrails.py:115-117)
-        printit = (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
-                   "{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
-                   "{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
-        if FORMAT_HEADER_VALUES:
-            printit = (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
-                       f"{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
-                       f"{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
-        return img, printit
+        big_endian = False
+        if raw and hasattr(fitsio, "read_raw_image"):
+            try:
+                img, h = fitsio.read_raw_image(fitspath)
+                big_endian = True
+            except ValueError:           # not a plain BITPIX=-32 image: decode on the host
+                img = fitsio.read(fitspath)
+                h = fitsio.read_header(fitspath)
+        else:
+            img = fitsio.read(fitspath)
+            h = fitsio.read_header(fitspath)
+        if not big_endian and img.dtype != _np.float32:
+            img = img.astype(_np.float32)
+        printit = _results_prefix(run, camcol, filter, field, h)
+        return (img, printit, big_endian) if raw else (img, printit)
     finally:
         if removefits:
             os.remove(fitspath)
-
-
-_handles = {}
-
-
-def _batch_handle(shape, batch, device):
-    key = (shape, device)
-    h = _handles.get(key)
-    if h is None or h.B < batch:
-        if h is not None:
-            h.close()
-        h = _lib.Handle(shape[0], shape[1], max_batch=batch, device=device)
-        _handles[key] = h
-    return h
 
 
 def _error_text(run, camcol, filter, field, exc):
@@ -118,70 +109,206 @@ def _error_text(run, camcol, filter, field, exc):
             "".join(traceback.format_exception(type(exc), exc, exc.__traceback__, limit=3)) + str(exc) + "\n\n")
 
 
-def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0):
+def _results_prefix(run, camcol, filter, field, h):
+    """The header part of the results line (detecttrails.py:115-117); only the first fragment is an f-string in the
+    reference, the seven other brace groups are literal text and stay literal unless FORMAT_HEADER_VALUES is set."""
+    if FORMAT_HEADER_VALUES:
+        return (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
+                f"{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
+                f"{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
+    return (f"{run} {camcol} {filter} {field} {h['TAI']} {h['CRPIX1']} "
+            "{h['CRPIX2']} {h['CRVAL1']} {h['CRVAL2']} {h['CD1_1']} "
+            "{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
+
+
+def _load_one(frame, params_removestars, slot=None):
+    """Host side of one frame (runs in a loader thread): FITS image + header line prefix, photoObj catalog -> blot
+    rectangles.  With ``slot`` (a row of a handle's pinned staging viewed as uint32) an uncompressed frame of that
+    shape is read straight into it as raw big-endian payload.
+    Returns ("staged", None, True, rects, printit) | ("ok", pixels, big_endian, rects, printit) | ("err", exc)."""
+    run, camcol, filter, field = frame
+    try:
+        staged = False
+        if slot is not None and hasattr(fitsio, "read_raw_image_into"):
+            path = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
+            if os.path.exists(path):
+                try:
+                    h = fitsio.read_raw_image_into(path, slot)
+                    printit = _results_prefix(run, camcol, filter, field, h)
+                    staged = True
+                except ValueError:
+                    staged = False
+        if not staged:
+            img, printit, big_endian = _load_frame(run, camcol, filter, field, raw=True)
+        cat = read_photoObj_arrays(files.filename("photoObj", run=run, camcol=camcol, field=field))
+        shape = slot.shape if staged else img.shape
+        rects = star_rects(cat, filter, shape, **dict(params_removestars))
+        if staged:
+            return ("staged", None, True, rects, printit)
+        return ("ok", img, big_endian, rects, printit)
+    except Exception as e:   # noqa: BLE001 - the reference swallows everything per frame
+        return ("err", e)
+
+
+_handles = {}
+N_RING = 3      # handles per frame shape: one computing, one submitted (crossing PCIe), one being filled by the loaders
+
+
+def _batch_handles(shape, batch, device, count=N_RING):
+    key = (shape, device)
+    hs = _handles.get(key)
+    if hs is None or hs[0].B < batch or len(hs) < count:
+        for h in hs or []:
+            h.close()
+        hs = [_lib.Handle(shape[0], shape[1], max_batch=batch, device=device) for _ in range(count)]
+        _handles[key] = hs
+    return hs
+
+
+def _probe_shape(frames):
+    """Shape of the first readable frame (SDSS frames of a run all have one shape); None if none can be read."""
+    for (run, camcol, filter, field) in frames[:8]:
+        try:
+            path = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
+            if os.path.exists(path):
+                h = fitsio.read_header(path)
+                return (int(h["NAXIS2"]), int(h["NAXIS1"]))
+        except Exception:   # noqa: BLE001
+            continue
+    return None
+
+
+def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0, loaders=None):
     """Run an ordered list of (run, camcol, filter, field) through the GPU in batches.  Returns one record per
     frame, in list order: ("line", results_line) for a detection, ("none", "") for no detection,
-    ("err", errors_text) for a failure - exactly what the reference's per-frame loop would append."""
+    ("err", errors_text) for a failure - exactly what the reference's per-frame loop would append.
+
+    Pipeline (three handles of the common frame shape form a ring): while batch k-1 computes and batch k crosses
+    PCIe, loader threads read the FITS payloads of batch k+1 straight into the third handle's pinned staging
+    (raw big-endian bytes, `readinto`, no GIL; the first kernel byte-swaps) and filter the catalogs.  Frames that
+    are compressed, of another shape or another BITPIX take the decoded-array path through the same ring."""
+    from concurrent.futures import ThreadPoolExecutor
     debug = bool(params_bright["debug"] or params_dim["debug"])
     frames = list(frames)
-    records = []
-    for i0 in range(0, len(frames), batch):
-        chunk = frames[i0:i0 + batch]
-        loaded = []          # per frame: ("ok", img, rects, printit) or ("err", exc)
-        for (run, camcol, filter, field) in chunk:
+    batch = max(int(batch), 1)
+    chunks = [frames[i:i + batch] for i in range(0, len(frames), batch)]
+    records = [None] * len(frames)
+    outcome = {}             # global frame index -> ("ok", detected, result dict) | ("err", exc)
+    loaded_all = {}          # global frame index -> loader result
+    pending = []             # in-flight device batches: (handle, shape, [global indices])
+    shape0 = _probe_shape(frames)
+    ring = []
+    if shape0 is not None:
+        try:
+            ring = _batch_handles(shape0, batch, device)
+        except Exception:   # noqa: BLE001 - reported per frame below, when the submit fails the same way
+            ring = []
+
+    def collect(entry):
+        h, shape, gidx = entry
+        try:
+            res = h.wait()
+        except Exception as e:   # noqa: BLE001
+            for g in gidx:
+                outcome[g] = ("err", e)
+            return
+        for k, g in enumerate(gidx):
             try:
-                img, printit = _load_frame(run, camcol, filter, field)
-                cat = read_photoObj_arrays(files.filename("photoObj", run=run, camcol=camcol, field=field))
-                rp = {k: v for k, v in params_removestars.items()}
-                rects = star_rects(cat, filter, img.shape, **rp)
-                if img.dtype != _np.float32:
-                    img = img.astype(_np.float32)
-                loaded.append(("ok", img, rects, printit))
-            except Exception as e:   # noqa: BLE001 - the reference swallows everything per frame
-                loaded.append(("err", e))
-        # frames of one shape go to the device together
-        by_shape = {}
-        for j, item in enumerate(loaded):
-            if item[0] == "ok":
-                by_shape.setdefault(item[1].shape, []).append(j)
-        outcome = {}
-        for shape, idxs in by_shape.items():
-            try:
-                h = _batch_handle(shape, max(batch, 1), device)
-                h.set_params(params_bright, params_dim)
-                for k, j in enumerate(idxs):
-                    h.host_frames[k] = loaded[j][1]
-                h.submit(len(idxs), [loaded[j][2] for j in idxs], flags=0)
-                res = h.wait()
-                for k, j in enumerate(idxs):
-                    try:
-                        r = res[k]
-                        if r.status & _lib.FRAME_OVERFLOW:
-                            raise _lib.LfdError(_lib.LFD_E_CAPACITY, "per-frame work list overflow")
-                        det, out = (False, None)
-                        for p in (0, 1):
-                            if r.rect_detection[p] >= 0:
-                                det, out = result_from_device(r, p, shape)
-                                if det:
-                                    break
-                        outcome[j] = ("ok", det, out)
-                    except Exception as e:   # noqa: BLE001
-                        outcome[j] = ("err", e)
+                r = res[k]
+                if r.status & _lib.FRAME_OVERFLOW:
+                    raise _lib.LfdError(_lib.LFD_E_CAPACITY, "per-frame work list overflow")
+                det, out = (False, None)
+                for p in (0, 1):
+                    if r.rect_detection[p] >= 0:
+                        det, out = result_from_device(r, p, shape)
+                        if det:
+                            break
+                outcome[g] = ("ok", det, out)
             except Exception as e:   # noqa: BLE001
-                for j in idxs:
-                    outcome[j] = ("err", e)
-        for j, (run, camcol, filter, field) in enumerate(chunk):
-            item = loaded[j]
-            exc = item[1] if item[0] == "err" else (outcome[j][1] if outcome[j][0] == "err" else None)
-            if exc is not None:
-                if debug:
-                    traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
-                records.append(("err", _error_text(run, camcol, filter, field, exc)))
-            elif outcome[j][1]:
-                res = outcome[j][2]
-                records.append(("line", item[3] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n"))
+                outcome[g] = ("err", e)
+
+    def release(h):
+        for entry in [e for e in pending if e[0] is h]:
+            collect(entry)
+            pending.remove(entry)
+
+    def submit(h, shape, gidx, rects, big_endian):
+        try:
+            h.set_params(params_bright, params_dim)
+            h.submit(len(gidx), rects, flags=_lib.INPUT_BIGENDIAN if big_endian else 0)
+            pending.append((h, shape, gidx))
+        except Exception as e:   # noqa: BLE001
+            for g in gidx:
+                outcome[g] = ("err", e)
+
+    nload = loaders or max(2, min(8, (os.cpu_count() or 2)))
+    with ThreadPoolExecutor(max_workers=nload) as pool:
+        futs = {}
+
+        def prefetch(ci):
+            if ci >= len(chunks) or ci in futs:
+                return
+            h = ring[ci % len(ring)] if ring else None
+            if h is not None:
+                release(h)                                   # its previous batch (ci - N_RING) is long done
+                st = h.host_frames.view(_np.uint32)
+                futs[ci] = [pool.submit(_load_one, fr, params_removestars, st[j]) for j, fr in enumerate(chunks[ci])]
             else:
-                records.append(("none", ""))
+                futs[ci] = [pool.submit(_load_one, fr, params_removestars, None) for fr in chunks[ci]]
+
+        prefetch(0)
+        for ci, chunk in enumerate(chunks):
+            prefetch(ci + 1)
+            loaded = [f.result() for f in futs.pop(ci)]
+            base = ci * batch
+            for j, item in enumerate(loaded):
+                loaded_all[base + j] = item
+            h = ring[ci % len(ring)] if ring else None
+            staged = [j for j, it in enumerate(loaded) if it[0] == "staged"]
+            others = {}
+            for j, it in enumerate(loaded):
+                if it[0] == "ok":
+                    others.setdefault((it[1].shape, it[2]), []).append(j)
+            if staged:
+                # staged frames sit in their own slots; compact them to the front (a frame that failed or took the
+                # other path leaves a hole)
+                st = h.host_frames.view(_np.uint32)
+                for k, j in enumerate(staged):
+                    if k != j:
+                        st[k] = st[j]
+                submit(h, shape0, [base + j for j in staged], [loaded[j][3] for j in staged], True)
+            for (shape, big_endian), idxs in others.items():
+                gidx = [base + j for j in idxs]
+                try:
+                    if h is not None and shape == shape0 and not staged:
+                        hh = h
+                    else:
+                        # rare: another frame shape, or a second group in this chunk -> a handle of its own, synchronously
+                        hh = _lib.Handle(shape[0], shape[1], max_batch=len(idxs), device=device)
+                    stg = hh.host_frames.view(_np.uint32) if big_endian else hh.host_frames
+                    for slot, j in enumerate(idxs):
+                        stg[slot] = loaded[j][1]
+                    submit(hh, shape, gidx, [loaded[j][3] for j in idxs], big_endian)
+                    if hh is not h:
+                        release(hh)
+                        hh.close()
+                except Exception as e:   # noqa: BLE001
+                    for g in gidx:
+                        outcome[g] = ("err", e)
+        for entry in list(pending):
+            collect(entry)
+    for g, (run, camcol, filter, field) in enumerate(frames):
+        item = loaded_all[g]
+        exc = item[1] if item[0] == "err" else (outcome[g][1] if outcome[g][0] == "err" else None)
+        if exc is not None:
+            if debug:
+                traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
+            records[g] = ("err", _error_text(run, camcol, filter, field, exc))
+        elif outcome[g][1]:
+            res = outcome[g][2]
+            records[g] = ("line", item[4] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n")
+        else:
+            records[g] = ("none", "")
     return records
 
 

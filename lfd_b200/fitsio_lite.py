@@ -220,6 +220,30 @@ def read_raw_image(path):
     raise OSError("no image HDU in %s" % path)
 
 
+def read_raw_image_into(path, dest):
+    """Like read_raw_image, but the payload is read straight into ``dest`` (a writable C-contiguous uint32 array of
+    shape (NAXIS2, NAXIS1), e.g. a slot of the library's pinned staging) with ``readinto`` - no intermediate copy and
+    no GIL while the bytes move.  Returns the header; raises ValueError if the image does not fit ``dest``."""
+    for h, pos, nbytes in _iter_hdus(path):
+        if nbytes == 0:
+            continue
+        if h["BITPIX"] != -32 or h["NAXIS"] != 2:
+            raise ValueError("raw upload path needs a 2-D BITPIX=-32 image")
+        if (h["NAXIS2"], h["NAXIS1"]) != tuple(dest.shape) or dest.dtype.itemsize != 4:
+            raise ValueError("image shape %s does not match the staging slot %s" % ((h["NAXIS2"], h["NAXIS1"]), dest.shape))
+        with open(path, "rb", buffering=0) as f:
+            f.seek(pos)
+            mv = memoryview(dest).cast("B")
+            got = 0
+            while got < nbytes:
+                k = f.readinto(mv[got:nbytes])
+                if not k:
+                    raise OSError("short read in %s" % path)
+                got += k
+        return h
+    raise OSError("no image HDU in %s" % path)
+
+
 # ----------------------------------------------------------------------------------------------
 # writers (used by the synthetic SDSS tree generator and the tests)
 # ----------------------------------------------------------------------------------------------

@@ -52,8 +52,8 @@ def star_rects(cat, _filter, shape, defaultxy, filter_caps, maxxy, pixscale, mag
     """Blot rectangles (row_start, row_stop, col_start, col_stop) on the un-flipped image.
 
     Filter logic of removestars.py:212-230, vectorised; the slice ``img[x-dxy:x+dxy, y-dxy:y+dxy]``
-    (:231) is resolved with Python's own slice arithmetic so that objects whose start goes negative
-    wrap to an empty slice exactly like NumPy's indexing does."""
+    (:231) is resolved with Python's slice arithmetic (vectorised ``slice.indices``) so that objects whose start
+    goes negative wrap to an empty slice exactly like NumPy's indexing does."""
     b = _BANDS.index(_filter)
     H, W = shape
     rows = _ceil_int(cat["ROWC"]); cols = _ceil_int(cat["COLC"])
@@ -72,14 +72,17 @@ def star_rects(cat, _filter, shape, defaultxy, filter_caps, maxxy, pixscale, mag
     pos = p90[:, b] > 0
     dxy[pos] = (p90[pos, b] / pixscale).astype(np.int64) + 10     # int() truncation of a positive float
     dxy[dxy > maxxy] = defaultxy
-    out = []
-    x, y = cols[:, b], rows[:, b]
-    for i in np.flatnonzero(keep):
-        r0, r1, _ = slice(int(x[i] - dxy[i]), int(x[i] + dxy[i])).indices(H)
-        c0, c1, _ = slice(int(y[i] - dxy[i]), int(y[i] + dxy[i])).indices(W)
-        if r0 < r1 and c0 < c1:
-            out.append((r0, r1, c0, c1))
-    return np.asarray(out, np.int32).reshape(-1, 4)
+    x, y = cols[keep, b], rows[keep, b]
+    dk = dxy[keep]
+
+    def resolve(v, length):
+        # slice.indices() for step 1: a negative bound counts from the end, then both are clamped to [0, length]
+        return np.clip(np.where(v < 0, v + length, v), 0, length)
+
+    r0, r1 = resolve(x - dk, H), resolve(x + dk, H)
+    c0, c1 = resolve(y - dk, W), resolve(y + dk, W)
+    ok = (r0 < r1) & (c0 < c1)
+    return np.stack([r0[ok], r1[ok], c0[ok], c1[ok]], axis=1).astype(np.int32).reshape(-1, 4)
 
 
 def remove_stars(img, _run, _camcol, _filter, _field, defaultxy, filter_caps, maxxy, pixscale, magcount,
