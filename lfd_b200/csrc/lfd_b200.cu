@@ -376,8 +376,18 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_prep<2>, 256, 0));
         for (int m = 0; m < 3; m++) h->prep_grid[m] = prop.multiProcessorCount * (per_sm[m] > 0 ? per_sm[m] : 1);
     }
-    CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
-    CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_smem(max_batch)));
+    // the dynamic shared-memory limit is a property of the FUNCTION, shared by every handle of the process: only ever raise it
+    {
+        static size_t band_max = 48 * 1024, rects_max = 48 * 1024;
+        if (ccl_band_smem(h->d.WW) > band_max) {
+            band_max = ccl_band_smem(h->d.WW);
+            CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_max));
+        }
+        if (rects_smem(max_batch) > rects_max) {
+            rects_max = rects_smem(max_batch);
+            CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_max));
+        }
+    }
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
     for (int i = 0; i < 4; i++) { CK(cudaEventCreate(&h->mark[i])); h->mark_valid[i] = true; }
 
