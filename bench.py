@@ -422,7 +422,8 @@ def run_ours(args):
     prep_bytes = B * (4 * N + 2 * N)
     prep_ms = prep_ms_sum / args.steps               # measured live in the timed region
     stage_report = []
-    alg = {"lut+morph": 2 * N + 2 * N, "sobel+nms": 2 * N, "ccl_fg(hysteresis)": 9 * N // 2, "ccl_bg(holes)": 9 * N // 2,
+    # S2 LUT apply 2N + S4 dilate 2N (+ S3 erode 2N in the dim pass), S5 2N, S6 9N for fg+bg, S8 1N
+    alg = {"lut+morph": 2 * N + 2 * N, "dim:lut+morph": 2 * N + 2 * N + 2 * N, "sobel+nms": 2 * N, "ccl_fg(hysteresis)": 9 * N // 2, "ccl_bg(holes)": 9 * N // 2,
            "rects+boxfill": N}
     for name, ms in stage_ms:
         entry = {"stage": name, "ms_per_step": round(ms, 4)}
@@ -430,13 +431,17 @@ def run_ours(args):
         nfr = n_bright if name.startswith("bright") else n_dim if name.startswith("dim") else B
         if name.startswith("prep"):
             entry.update(bytes=prep_bytes, gbs=prep_bytes / (ms * 1e6) if ms > 0 else None)
-        elif key in alg and ms > 0:
-            by = nfr * alg[key]
+        elif (name in alg or key in alg) and ms > 0:
+            by = nfr * alg.get(name, alg.get(key))
             entry.update(bytes=by, gbs=by / (ms * 1e6))
         if entry.get("gbs"):
             entry["frac_of_hbm_peak"] = entry["gbs"] / peak
         stage_report.append(entry)
     hough_ms = per["bright:hough"] + per["dim:hough"]
+    try:
+        smem_peak = hA.smem_atomic_peak()
+    except Exception:   # noqa: BLE001
+        smem_peak = None
     roofline = {"bound": "hbm", "kernel": "k_prep", "achieved": prep_bytes / (prep_ms * 1e6), "peak": peak, "unit": "GB/s",
                 "frac": prep_bytes / (prep_ms * 1e6) / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": prep_bytes,
@@ -496,7 +501,11 @@ def run_ours(args):
                        "in the timed region the bright and dim passes overlap on two streams" % (n_serial, serial_ms),
         "hough": {"ms_per_step": hough_ms, "votes_per_step": counters["votes"],
                   "gvotes_per_s": counters["votes"] / (hough_ms * 1e6) if hough_ms > 0 else None,
-                  "frames_hough": counters["frames_hough"]},
+                  "frames_hough": counters["frames_hough"],
+                  "smem_atomic_peak_gops": smem_peak,
+                  "note": "votes = non-zero pixels x 180 angles of the frames that reach HoughLines; a vote kernel that issued one "
+                          "shared-memory atomic per vote could not exceed smem_atomic_peak_gops (measured by a conflict-free micro-"
+                          "kernel on all SMs); this design issues one atomic per (32-pixel mask word, angle, rho bin)"},
         "counters": counters,
         "cpu_baseline": cpu_baseline,
         "dropin_e2e": dropin,

@@ -194,6 +194,10 @@ int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, int width, do
  * of the handle's frame size; edges_out: uint8 height*width, 0 / 255.  (Config-5 microbenchmark and parity.) */
 int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, uint8_t* edges_out);
 
+/* Micro-benchmark: peak shared-memory atomicAdd rate of the device in G atomics/s (conflict-free, all SMs) - the
+ * roofline the Hough vote kernel (shared-memory-privatised accumulators) is reported against. */
+int lfd_smem_atomic_peak(lfd_handle* h, double* gops);
+
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
 const char* lfd_timing_name(int i);

@@ -115,6 +115,7 @@ def lib():
                                       ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
         L.lfd_canny.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.lfd_smem_atomic_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -314,6 +315,12 @@ class Handle:
         out = np.empty((self.H, self.W), np.uint8)
         self._ck(self._L.lfd_canny(self.h, img.ctypes.data_as(ctypes.c_void_p), int(low), int(high), out.ctypes.data_as(ctypes.c_void_p)))
         return out
+
+    def smem_atomic_peak(self):
+        """Measured peak shared-memory atomicAdd rate of the device, G atomics / s."""
+        g = ctypes.c_double()
+        self._ck(self._L.lfd_smem_atomic_peak(self.h, ctypes.byref(g)))
+        return float(g.value)
 
     def timings(self):
         ms = (ctypes.c_float * 32)()

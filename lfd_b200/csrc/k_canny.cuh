@@ -197,12 +197,16 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
     __syncwarp();
     const int TG22 = 13573;
     // rows are requested NMS_PF steps ahead of their use (software pipeline; the kernel is latency-bound)
+    // every lane issues the same kind of load (lanes left / right of the frame read the edge word pair), so the
+    // prefetch covers them too; BORDER_REPLICATE is applied when the row is consumed (fix_row)
+    const int wxc = min(max(wx, 0), Ww - 2);
     auto load_row = [&](int yi) -> uint2 {
         const int yl = min(max(yi, 0), d.H - 1);                     // BORDER_REPLICATE rows
-        uint2 v;
-        if (col_in) v = __ldg(g + (((size_t)yl * Ww + wx) >> 1));
-        else {                                                       // BORDER_REPLICATE columns
-            u32 e = (wx < 0) ? (__ldg(gw + (size_t)yl * Ww) & 0xffu) : (__ldg(gw + (size_t)yl * Ww + Ww - 1) >> 24);
+        return __ldg(g + (((size_t)yl * Ww + wxc) >> 1));
+    };
+    auto fix_row = [&](uint2 v) -> uint2 {
+        if (!col_in) {                                               // BORDER_REPLICATE columns
+            u32 e = (wx < 0) ? (v.x & 0xffu) : (v.y >> 24);
             v.x = v.y = e * 0x01010101u;
         }
         return v;
@@ -221,7 +225,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const int yi = yb + u;
-            const uint2 v = cur[u];
+            const uint2 v = fix_row(cur[u]);
             const int sa = (u + 1) % 3, sb = (u + 2) % 3, sc = u % 3;   // ring slots of rows yi-2, yi-1, yi
             rz[sc] = !__any_sync(FULLMASK, (v.x | v.y) != 0u);
             if (rz[0] && rz[1] && rz[2]) {
@@ -281,7 +285,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                 const u32 bal = __ballot_sync(FULLMASK, nzf[sa]);
                 u32 myc = 0, mys = 0;                                // lane g keeps mask word g
                 const u16* Mu = sM[wid][sc]; const u16* Mc = sM[wid][sa]; const u16* Md = sM[wid][sb];
-#pragma unroll
+#pragma unroll 1
                 for (int gi = 0; gi < 7; gi++) {
                     int cls = 0;
                     if ((bal >> (2 + 4 * gi)) & 0xfu) {              // some pixel of this 32-px group has a gradient

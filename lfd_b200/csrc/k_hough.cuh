@@ -309,3 +309,23 @@ __global__ void k_check_theta(lfd_result* __restrict__ res, FrameCtl* __restrict
     if (c->hough[pass]) atomicAdd(&counters[8], 1ull);
     atomicAdd(&counters[9 + pass], 1ull);
 }
+
+
+// Peak shared-memory atomic throughput of this GPU (the roofline the Hough vote kernel is measured against):
+// every lane adds to its own bank-conflict-free word, `iters` times, on all SMs.
+__global__ void __launch_bounds__(256)
+k_smem_atomic_peak(int iters, unsigned* sink)
+{
+    __shared__ unsigned acc[256 * 8];
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    unsigned* p = acc + threadIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) atomicAdd(p + 256 * k, 1u);
+    }
+    __syncthreads();
+    unsigned v = 0;
+    for (int k = 0; k < 8; k++) v += acc[threadIdx.x + 256 * k];
+    if (v == 0xffffffffu) sink[0] = v;       // never true: keeps the loop alive
+}

@@ -1069,6 +1069,34 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// micro-benchmark: peak shared-memory atomic rate (denominator for the Hough vote kernel)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_smem_atomic_peak(lfd_handle* h, double* gops)
+{
+    if (!h || !gops) return LFD_E_ARG;
+    cudaSetDevice(h->device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    k_smem_atomic_peak<<<blocks, 256, 0, h->stream>>>(64, (unsigned*)h->counters_d + 30); LAUNCH_CHECK();      // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        CK(cudaEventRecord(a, h->stream));
+        k_smem_atomic_peak<<<blocks, 256, 0, h->stream>>>(iters, (unsigned*)h->counters_d + 30); LAUNCH_CHECK();
+        CK(cudaEventRecord(b, h->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *gops = (double)blocks * 256.0 * 8.0 * iters / (best * 1e6);
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------------
 extern "C" int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries)

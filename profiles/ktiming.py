@@ -15,6 +15,13 @@ from oracle import ref_pipeline as rp  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 frames, cats, rects, kinds = bench.make_pool(B, 0)
+if os.environ.get("KIND"):           # e.g. KIND=sparse / KIND=dense: a batch of one kind of field only
+    from lfd_b200 import synth
+    from lfd_b200.removestars import star_rects
+    frames, rects = [], []
+    for i in range(B):
+        img, cat = synth.make_case(os.environ["KIND"], 9000 + i % 8)
+        frames.append(img); rects.append(star_rects(cat, "r", img.shape, **rp.DEFAULT_REMOVESTARS))
 h = _lib.Handle(bench.H, bench.W, max_batch=B)
 h.set_params(dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM))
 for i, f in enumerate(frames):
