@@ -55,7 +55,8 @@ struct lfd_handle {
     bool have_params = false;
     cudaStream_t stream = nullptr;        // uploads, prep, bright pass, results
     cudaStream_t stream2 = nullptr;       // dim pass, overlapped with the bright pass
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr, stream4 = nullptr;   // second half of the batch (bright, dim)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     std::string err;
     int64_t launches = 0;
     int last_n = 0, last_flags = 0;
@@ -317,6 +318,8 @@ extern "C" int lfd_destroy(lfd_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->stream3) cudaStreamSynchronize(h->stream3);
+    if (h->stream4) cudaStreamSynchronize(h->stream4);
     for (void* p : h->allocs) cudaFree(p);
     for (int p = 0; p < 2; p++) {
         if (h->hb[p].accum) cudaFree(h->hb[p].accum);
@@ -335,6 +338,10 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
+    if (h->ev_join4) cudaEventDestroy(h->ev_join4);
+    if (h->stream4) cudaStreamDestroy(h->stream4);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -365,6 +372,10 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     {
@@ -551,12 +562,27 @@ extern "C" int lfd_set_params(lfd_handle* h, const lfd_params* p)
 // ------------------------------------------------------------------------------------------------
 // the pipeline
 // ------------------------------------------------------------------------------------------------
-static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStream_t s, bool stage_events)
+// frames [f0, f0 + n) of the batch: every per-frame array is entered at frame f0, kernels index frames from 0
+static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, cudaStream_t s, bool stage_events)
 {
 #define STAGE_EVENT(i) do { if (stage_events) CK(cudaEventRecord(h->ev[i], s)); } while (0)
     const Dims d = h->d;
     const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
-    FrameCtl* const C = h->ctl + (size_t)pass * h->B;      // this pass's bookkeeping block
+    FrameCtl* const C = h->ctl + (size_t)pass * h->B + f0;      // this pass's bookkeeping block
+    const size_t fN = (size_t)f0 * d.N, fNW = (size_t)f0 * d.NW;
+    u8* const v_gray = h->gray[pass] + fN;
+    u8* const v_morph = h->morph[pass] + fN;
+    u32* const v_nz = h->nz[pass] + fNW;
+    u32* const v_cand = h->cand[pass] + fNW;
+    u32* const v_strong = h->strong[pass] + fNW;
+    u32* const v_edges = h->edges[pass] + fNW;
+    u32* const v_box = h->box[pass] + fNW;
+    CclBuf* const v_ccl0 = h->ccl_d[pass][0] + f0;
+    CclBuf* const v_ccl1 = h->ccl_d[pass][1] + f0;
+    CompBuf* const v_comp = h->comp_d[pass] + f0;
+    RectBuf* const v_rbuf = h->rbuf_d[pass] + f0;
+    uint2* const v_segs = h->segs[pass] + (size_t)f0 * 2 * d.NW;
+    lfd_result* const v_res = h->res_d + f0;
     const bool taps = flags & LFD_KEEP_TAPS;
     const int tbase = 2 + pass * (T_PER_PASS - 1);   // event index preceding this pass's first stage
     HoughBufs& hb = h->hb[pass];
@@ -565,23 +591,23 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
     // LUT + morphology
-    k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist, h->lut, C, h->B, d.N, pass); LAUNCH_CHECK();
+    k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist + (size_t)f0 * 256, h->lut + (size_t)f0 * 256, C, h->B, d.N, pass); LAUNCH_CHECK();
     MorphCfg mc;
     mc.eh = pass ? pp.erode_h : 0; mc.ew = pass ? pp.erode_w : 0; mc.dh = pp.dilate_h; mc.dw = pp.dilate_w;
     u8* etap = nullptr;
     if (taps && pass == 1 && mc.eh > 0) {
         if (!h->eroded_tap) { int rc = dev_alloc(h, &h->eroded_tap, (size_t)h->B * d.N); if (rc) return rc; }
-        etap = h->eroded_tap;
+        etap = h->eroded_tap + fN;
     }
     {
-        const u8* lutp = h->lut + (size_t)pass * h->B * 256;
+        const u8* lutp = h->lut + ((size_t)pass * h->B + f0) * 256;
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + MARCH_R - 1) / MARCH_R;
         const int nunits = nstrips * nchunks;
         dim3 gg((nunits + 3) / 4, n);
         bool done = false;
 #define MORPH_CASE(EH_, EW_, DH_, DW_)                                                                              \
         if (!done && (d.W % 8) == 0 && mc.eh == EH_ && mc.ew == EW_ && mc.dh == DH_ && mc.dw == DW_) {                \
-            k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, \
+            k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(v_gray, lutp, v_morph, v_nz, etap, \
                                                                C, pass, d, nstrips, nunits);                    \
             done = true;                                                                                             \
         }
@@ -593,7 +619,7 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
 #undef MORPH_CASE
         if (!done) {                // any other all-ones rectangle: shared-memory tile kernel
             dim3 mg((d.W + MORPH_TW - 1) / MORPH_TW, (d.H + MORPH_TH - 1) / MORPH_TH, n);
-            k_morph<<<mg, 256, 0, s>>>(h->gray[pass], lutp, h->morph[pass], h->nz[pass], etap, C, pass, d, mc);
+            k_morph<<<mg, 256, 0, s>>>(v_gray, lutp, v_morph, v_nz, etap, C, pass, d, mc);
         }
         LAUNCH_CHECK();
     }
@@ -602,58 +628,60 @@ static int run_pass_kernels(lfd_handle* h, int n, int pass, int flags, cudaStrea
     u8* ntap = nullptr;
     if (taps) {
         if (!h->nms_tap[pass]) { int rc = dev_alloc(h, &h->nms_tap[pass], (size_t)h->B * d.N); if (rc) return rc; }
-        ntap = h->nms_tap[pass];
+        ntap = h->nms_tap[pass] + fN;
     }
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
         dim3 gg((nunits + 3) / 4, n);
-        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, nstrips, nunits, 0, 255);
-        else k_nms_march<false><<<gg, 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, nstrips, nunits, 0, 255);
+        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
+        else k_nms_march<false><<<gg, 128, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
     } else {
         dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
-        k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], ntap, C, pass, d, 0, 255);
+        k_canny_nms<<<cg, 256, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, 0, 255);
     }
     LAUNCH_CHECK();
     STAGE_EVENT(tbase + 2);
     // foreground runs: hysteresis + outer contours
-    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][0], C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_edges_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], h->comp_d[pass], C, pass, d); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][0], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl0, C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(v_strong, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_edges_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(v_ccl0, v_edges, v_comp, C, pass, d); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl0, v_comp, C, pass, d, 0); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 3);
     // background runs: hole contours
-    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][1], C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
-    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, h->ccl_d[pass][1], C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(h->edges[pass], h->ccl_d[pass][1], h->comp_d[pass], C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl1, C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
+    k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 4);
     // rectangles + box image
-    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(h->comp_d[pass], h->rbuf_d[pass], h->ccl_d[pass][0], h->ccl_d[pass][1], C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
-    CK(cudaMemsetAsync(h->box[pass], 0, (size_t)n * d.NW * sizeof(u32), s));
-    k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(h->rbuf_d[pass], h->box[pass], C, pass, d); LAUNCH_CHECK();
+    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(v_box, 0, (size_t)n * d.NW * sizeof(u32), s));
+    k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(v_rbuf, v_box, C, pass, d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 5);
     // Hough on the morphology output and on the box image
-    CK(cudaMemsetAsync(hb.accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
-    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(h->nz[pass], h->box[pass], h->segs[pass], C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
-    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(h->segs[pass], hb.accum, hb.tabSin, hb.tabCos, C, pass,
+    int* const v_accum = hb.accum + (size_t)f0 * 2 * hb.accum_stride;
+    u64* const v_keys = hb.keys + (size_t)f0 * 2 * hb.key_stride;
+    CK(cudaMemsetAsync(v_accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
+    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(v_nz, v_box, v_segs, C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
+    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(v_segs, v_accum, hb.tabSin, hb.tabCos, C, pass,
                                                                             hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
     int cells = hb.hc.numangle * hb.hc.numrho;
     int pblocks = (cells + 255) / 256; if (pblocks > 64) pblocks = 64;
-    k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(hb.accum, hb.keys, C, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
-    k_hough_topk<<<dim3(2, n), 256, 0, s>>>(hb.keys, h->res_d, C, pass, hb.hc, hb.key_stride, pp.nlinesInSet); LAUNCH_CHECK();
+    k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(v_accum, v_keys, C, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
+    k_hough_topk<<<dim3(2, n), 256, 0, s>>>(v_keys, v_res, C, pass, hb.hc, hb.key_stride, pp.nlinesInSet); LAUNCH_CHECK();
     if (flags & LFD_FULL_LINES) {
         if (!hb.lines) CK(cudaMalloc((void**)&hb.lines, (size_t)h->B * 2 * hb.line_stride * sizeof(float)));
-        k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(hb.keys, hb.lines, C, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
+        k_hough_sort<<<dim3(2, n), 1024, 0, s>>>(v_keys, hb.lines + (size_t)f0 * 2 * hb.line_stride, C, pass, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
     }
     STAGE_EVENT(tbase + 6);
-    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(h->res_d, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh,
+    k_check_theta<<<(n + 63) / 64, 64, 0, s>>>(v_res, C, pass, n, pp.nlinesInSet, pp.dro, pp.thetaTresh, pp.lineSetTresh,
                                               hb.hc.numangle, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 7);
     return LFD_OK;
@@ -710,13 +738,27 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     cudaStream_t s1 = overlap ? h->stream2 : s;
     h->stage_timings_valid = !graph;
     // everything from the fork to the result copies; captured into a CUDA graph when `graph`
+    // with overlap and a batch of >= 16 frames the batch is also cut in two halves: four independent chains
+    // (bright / dim x half) keep the SMs busy through the latency-bound CCL / geometry phases
+    const int nsplit = (overlap && n >= 16) ? 2 : 1;
+    const int nh0 = nsplit == 2 ? (n + 1) / 2 : n;
     auto passes = [&](bool stage_events) -> int {
         int rc2;
-        if (overlap) { CK(cudaEventRecord(h->ev_fork, s)); CK(cudaStreamWaitEvent(s1, h->ev_fork, 0)); }
-        if (mode != 2) { if ((rc2 = run_pass_kernels(h, n, 0, flags, s, stage_events)) != LFD_OK) return rc2; }
+        if (overlap) {
+            CK(cudaEventRecord(h->ev_fork, s));
+            CK(cudaStreamWaitEvent(s1, h->ev_fork, 0));
+            if (nsplit == 2) { CK(cudaStreamWaitEvent(h->stream3, h->ev_fork, 0)); CK(cudaStreamWaitEvent(h->stream4, h->ev_fork, 0)); }
+        }
+        if (mode != 2) { if ((rc2 = run_pass_kernels(h, 0, nh0, 0, flags, s, stage_events)) != LFD_OK) return rc2; }
         else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
-        if (mode != 1) { if ((rc2 = run_pass_kernels(h, n, 1, flags, s1, stage_events)) != LFD_OK) return rc2; }
+        if (mode != 1) { if ((rc2 = run_pass_kernels(h, 0, nh0, 1, flags, s1, stage_events)) != LFD_OK) return rc2; }
         else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+        if (nsplit == 2) {
+            if ((rc2 = run_pass_kernels(h, nh0, n - nh0, 0, flags, h->stream3, false)) != LFD_OK) return rc2;
+            if ((rc2 = run_pass_kernels(h, nh0, n - nh0, 1, flags, h->stream4, false)) != LFD_OK) return rc2;
+            CK(cudaEventRecord(h->ev_join3, h->stream3)); CK(cudaStreamWaitEvent(s, h->ev_join3, 0));
+            CK(cudaEventRecord(h->ev_join4, h->stream4)); CK(cudaStreamWaitEvent(s, h->ev_join4, 0));
+        }
         if (overlap) { CK(cudaEventRecord(h->ev_join, s1)); CK(cudaStreamWaitEvent(s, h->ev_join, 0)); }
         k_finalize<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
         CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
