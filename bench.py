@@ -39,8 +39,10 @@ def env_int(k, d):
 
 def make_pool(n, rank):
     """n distinct frames of the config-3 mix (seeded by run/camcol/filter/field), with their blot rects."""
+    import lfd_b200
     from lfd_b200.removestars import star_rects
-    from oracle.ref_pipeline import DEFAULT_REMOVESTARS
+    DEFAULT_REMOVESTARS = lfd_b200.default_params()[2]
+    DEFAULT_REMOVESTARS = {k: v for k, v in DEFAULT_REMOVESTARS.items() if k != "debug"}
     frames, cats, rects, kinds = [], [], [], []
     field = 11
     while len(frames) < n:
@@ -277,8 +279,8 @@ def dropin_leg(device, ndistinct=32, nfields=256, batch=32):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    import lfd_b200
     from lfd_b200 import _lib
-    from oracle import ref_pipeline as rp
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     distributed = world > 1
@@ -310,7 +312,7 @@ def run_ours(args):
         return float(t.item())
 
     frames, cats, rects, kinds = make_pool(B, rank)
-    pb, pd = dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM)
+    pb, pd, _pr = lfd_b200.default_params()     # the drop-in's own defaults (detecttrails.py:202-239)
     hA = _lib.Handle(H, W, max_batch=B, device=local)
     hB = _lib.Handle(H, W, max_batch=B, device=local)
     for h in (hA, hB):

@@ -184,7 +184,6 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
     }
 
     const uint2* g = reinterpret_cast<const uint2*>(img + (size_t)f * d.N);
-    const u32* gw = reinterpret_cast<const u32*>(img + (size_t)f * d.N);
     u32 HD[3][4], H3[3][4];
     bool nzf[3] = {false, false, false};          // this lane has a gradient pixel in the row of slot k
     bool nzf_any[3] = {false, false, false};      // ... some lane of the warp has (the smem row of slot k is not all-zero)

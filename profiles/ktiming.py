@@ -11,7 +11,9 @@ sys.path.insert(0, ROOT)
 os.environ["LFD_KTIMING"] = "1"
 import bench  # noqa: E402
 from lfd_b200 import _lib  # noqa: E402
-from oracle import ref_pipeline as rp  # noqa: E402
+import lfd_b200  # noqa: E402
+PB, PD, PR = lfd_b200.default_params()
+PR = {k: v for k, v in PR.items() if k != "debug"}
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 frames, cats, rects, kinds = bench.make_pool(B, 0)
@@ -21,9 +23,9 @@ if os.environ.get("KIND"):           # e.g. KIND=sparse / KIND=dense: a batch of
     frames, rects = [], []
     for i in range(B):
         img, cat = synth.make_case(os.environ["KIND"], 9000 + i % 8)
-        frames.append(img); rects.append(star_rects(cat, "r", img.shape, **rp.DEFAULT_REMOVESTARS))
+        frames.append(img); rects.append(star_rects(cat, "r", img.shape, **PR))
 h = _lib.Handle(bench.H, bench.W, max_batch=B)
-h.set_params(dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM))
+h.set_params(PB, PD)
 for i, f in enumerate(frames):
     h.host_frames[i] = f
 h.upload(B, rects)
