@@ -100,7 +100,7 @@ typedef struct lfd_pass_params {
     int32_t nlinesInSet;        /* <= LFD_MAX_SET_LINES */
     int32_t contoursMode;       /* cv2.RETR_*: LIST(1) and CCOMP(2), TREE(3) give the same set; EXTERNAL(0) unsupported */
     int32_t contoursMethod;     /* cv2.CHAIN_APPROX_NONE(1) or SIMPLE(2) (same hulls); TC89_* unsupported */
-    int32_t erode_h, erode_w;   /* 0,0 = no erosion (bright).  Kernels must be all-ones rectangles. */
+    int32_t erode_h, erode_w;   /* 0,0 = no erosion (bright).  All-ones rectangles; other shapes: lfd_set_kernels. */
     int32_t dilate_h, dilate_w;
     int32_t reserved;
 } lfd_pass_params;
@@ -156,6 +156,13 @@ int lfd_destroy(lfd_handle* h);
 const char* lfd_last_error(const lfd_handle* h);   /* h may be NULL: error of the last failed lfd_create */
 
 int lfd_set_params(lfd_handle* h, const lfd_params* p);
+
+/* Structuring elements that are not all-ones rectangles (cv2.getStructuringElement crosses / ellipses, hand-made
+ * masks), for one pass: row-major uint8 masks, non-zero = member, cv2's default anchor (kw/2, kh/2), sides 1..31.
+ * Call after lfd_set_params (which resets both passes to the all-ones rectangles of lfd_pass_params).
+ * erode_mask may be NULL (no erosion; always ignored for the bright pass, processfield.py:354). */
+int lfd_set_kernels(lfd_handle* h, int pass, const uint8_t* erode_mask, int erode_h, int erode_w,
+                    const uint8_t* dilate_mask, int dilate_h, int dilate_w);
 
 /* Pinned host staging owned by the library (frames in, `max_batch` slots of height*width float32). */
 int lfd_host_frames(lfd_handle* h, float** out);

@@ -100,6 +100,8 @@ def lib():
                                     ctypes.POINTER(ctypes.c_void_p)]
         L.lfd_destroy.argtypes = [ctypes.c_void_p]
         L.lfd_set_params.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lfd_set_kernels.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.lfd_host_frames.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
         L.lfd_submit.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lfd_upload.argtypes = L.lfd_submit.argtypes
@@ -132,9 +134,11 @@ def _kernel_hw(kernel, name):
     k = np.asarray(kernel)
     if k.ndim != 2 or k.size == 0:
         raise ValueError("%s must be a 2-D array" % name)
-    if not np.all(k != 0):
-        raise UnsupportedParameter(LFD_E_UNSUPPORTED, "%s: only all-ones rectangular kernels are implemented" % name)
     return int(k.shape[0]), int(k.shape[1])
+
+
+def _all_ones(kernel):
+    return kernel is None or bool(np.all(np.asarray(kernel) != 0))
 
 
 def pass_params(d, dim):
@@ -199,7 +203,27 @@ class Handle:
         if key == self._params_key:
             return
         P = Params(pass_params(params_bright, False), pass_params(params_dim, True))
+        # structuring elements that are not all-ones rectangles go through lfd_set_kernels; the rectangle sizes in
+        # the params struct are then placeholders (1x1) so that the rectangle path's halo limits do not apply
+        special = []
+        for pass_, (dct, pp) in enumerate(((params_bright, P.bright), (params_dim, P.dim))):
+            ek = dct.get("erodeKernel") if pass_ == 1 else None
+            dk = dct["dilateKernel"]
+            eh, ew = _kernel_hw(ek, "erodeKernel")
+            dh, dw = _kernel_hw(dk, "dilateKernel")
+            # the rectangle kernels stage a 16-row / 12-column halo; wider all-ones rectangles take the general path too
+            too_wide = (eh // 2 + dh // 2 > 16) or (ew // 2 + dw // 2 > 11)
+            if not (_all_ones(ek) and _all_ones(dk)) or too_wide:
+                special.append((pass_, None if ek is None else np.ascontiguousarray(np.asarray(ek) != 0, np.uint8),
+                                np.ascontiguousarray(np.asarray(dk) != 0, np.uint8)))
+                pp.dilate_h = pp.dilate_w = 1
+                if pass_ == 1 and ek is not None:
+                    pp.erode_h = pp.erode_w = 1
         self._ck(self._L.lfd_set_params(self.h, ctypes.byref(P)))
+        for pass_, ek, dk in special:
+            self._ck(self._L.lfd_set_kernels(self.h, pass_, None if ek is None else ek.ctypes.data_as(ctypes.c_void_p),
+                                             0 if ek is None else ek.shape[0], 0 if ek is None else ek.shape[1],
+                                             dk.ctypes.data_as(ctypes.c_void_p), dk.shape[0], dk.shape[1]))
         self._params_key = key
 
     @staticmethod

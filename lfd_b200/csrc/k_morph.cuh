@@ -369,3 +369,85 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
         }
     }
 }
+
+// ================================================================================================
+// Arbitrary structuring elements (cv2.getStructuringElement crosses / ellipses, hand-made masks):
+// direct evaluation over the list of non-zero kernel offsets on a shared-memory tile.  Slow path by
+// design - the all-ones rectangles the reference's defaults use never come here.
+// ================================================================================================
+#define ANYK_MAX 31                    // largest kernel side
+#define ANYK_TW 64
+#define ANYK_TH 16
+
+struct AnyKernel {
+    int n;                             // number of non-zero elements (0 = stage absent)
+    int reach;                         // max |offset|
+    signed char dx[ANYK_MAX * ANYK_MAX], dy[ANYK_MAX * ANYK_MAX];     // offsets relative to the anchor (kw/2, kh/2)
+};
+
+// dynamic smem: A = (TH + 2(re+rd)) x (TW + 2(re+rd)) bytes, B = (TH + 2rd) x (TW + 2rd) bytes
+__host__ __device__ inline size_t anyk_smem(int re, int rd)
+{
+    return (size_t)(ANYK_TH + 2 * (re + rd)) * (ANYK_TW + 2 * (re + rd)) + (size_t)(ANYK_TH + 2 * rd) * (ANYK_TW + 2 * rd) + 256;
+}
+
+__global__ void __launch_bounds__(256)
+k_morph_any(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict__ morph, u32* __restrict__ nz,
+            u8* __restrict__ eroded_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d,
+            const AnyKernel* __restrict__ ek, const AnyKernel* __restrict__ dk)
+{
+    const int f = blockIdx.z;
+    if (!ctl[f].active[pass]) return;
+    extern __shared__ u8 anysm[];
+    const int re = ek ? ek->reach : 0, rd = dk->reach;
+    const int ra = re + rd;
+    const int AW = ANYK_TW + 2 * ra, AH = ANYK_TH + 2 * ra, BW = ANYK_TW + 2 * rd, BH = ANYK_TH + 2 * rd;
+    u8* A = anysm;
+    u8* B = A + AW * AH;
+    u8* slut = B + BW * BH;
+    slut[threadIdx.x] = lut[(size_t)f * 256 + threadIdx.x];
+    const int tx0 = blockIdx.x * ANYK_TW, ty0 = blockIdx.y * ANYK_TH;
+    const u8* src = gray + (size_t)f * d.N;
+    if (ek && ek->n > 0) {
+        for (int i = threadIdx.x; i < AW * AH; i += blockDim.x) {
+            int r = i / AW, c = i - r * AW;
+            int y = ty0 - ra + r, x = tx0 - ra + c;
+            A[i] = (y >= 0 && y < d.H && x >= 0 && x < d.W) ? src[(size_t)y * d.W + x] : (u8)255;     // ignored by min
+        }
+        __syncthreads();
+        const int n = ek->n;
+        for (int i = threadIdx.x; i < BW * BH; i += blockDim.x) {
+            int r = i / BW, c = i - r * BW;
+            int y = ty0 - rd + r, x = tx0 - rd + c;
+            int v = 0;                                              // outside the frame: ignored by max
+            if (y >= 0 && y < d.H && x >= 0 && x < d.W) {
+                v = 255;
+                for (int k = 0; k < n; k++) v = min(v, (int)A[(r + re + ek->dy[k]) * AW + (c + re + ek->dx[k])]);
+            }
+            B[i] = (u8)v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < BW * BH; i += blockDim.x) {
+            int r = i / BW, c = i - r * BW;
+            int y = ty0 - rd + r, x = tx0 - rd + c;
+            B[i] = (y >= 0 && y < d.H && x >= 0 && x < d.W) ? src[(size_t)y * d.W + x] : (u8)0;
+        }
+    }
+    __syncthreads();
+    const int n = dk->n;
+    for (int i = threadIdx.x; i < ANYK_TW * ANYK_TH; i += blockDim.x) {
+        int r = i / ANYK_TW, c = i - r * ANYK_TW;          // a warp covers 32 consecutive pixels of one row
+        int y = ty0 + r, x = tx0 + c;
+        const bool in = y < d.H && x < d.W;
+        int o = 0;
+        if (in) {
+            int v = 0;
+            for (int k = 0; k < n; k++) v = max(v, (int)B[(r + rd + dk->dy[k]) * BW + (c + rd + dk->dx[k])]);
+            o = slut[v];
+            morph[(size_t)f * d.N + (size_t)y * d.W + x] = (u8)o;
+            if (eroded_tap) eroded_tap[(size_t)f * d.N + (size_t)y * d.W + x] = slut[B[(r + rd) * BW + (c + rd)]];
+        }
+        u32 b = __ballot_sync(FULLMASK, in && o != 0);
+        if (lane_id() == 0 && y < d.H && (x >> 5) < d.WW) nz[(size_t)f * d.NW + (size_t)y * d.WW + (x >> 5)] = b;
+    }
+}

@@ -112,6 +112,10 @@ struct lfd_handle {
     int graph_n = 0, graph_flags = 0;
     int64_t graph_launches = 0;
     bool stage_timings_valid = true;
+    // arbitrary structuring elements (lfd_set_kernels): [pass][0 erode / 1 dilate]; n == 0 -> the all-ones rectangle of lfd_pass_params
+    AnyKernel* anyk_d = nullptr;      // [2][2]
+    AnyKernel anyk_h[2][2];
+    bool anyk_on[2] = {false, false};
     int prep_grid[3] = {0, 0, 0};     // resident CTAs of k_prep<mode> on this device (one full wave)
     cudaEvent_t mark[4];              // caller-placed timestamps on the handle's stream (lfd_timer_mark)
     bool mark_valid[4];
@@ -423,6 +427,8 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     }
     DA(h->tap_u8, N);
     DA(h->ctl, (size_t)2 * B);
+    DA(h->anyk_d, 4);
+    memset(h->anyk_h, 0, sizeof(h->anyk_h));
     DA(h->res_d, (size_t)B);
     DA(h->counters_d, 16);
     DA(h->segs[0], (size_t)B * 2 * NW);
@@ -555,7 +561,46 @@ extern "C" int lfd_set_params(lfd_handle* h, const lfd_params* p)
     }
     h->params = *p;
     h->have_params = true;
+    h->anyk_on[0] = h->anyk_on[1] = false;       // back to all-ones rectangles until lfd_set_kernels says otherwise
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // kernel arguments changed
+    return LFD_OK;
+}
+
+static int fill_anykernel(lfd_handle* h, AnyKernel* k, const uint8_t* mask, int kh, int kw, const char* what)
+{
+    memset(k, 0, sizeof(*k));
+    if (!mask || kh == 0 || kw == 0) return LFD_OK;
+    if (kh < 1 || kw < 1 || kh > ANYK_MAX || kw > ANYK_MAX) { h->err = std::string(what) + ": kernel side must be 1..31"; return LFD_E_UNSUPPORTED; }
+    const int ay = kh / 2, ax = kw / 2;        // cv2's default anchor
+    for (int i = 0; i < kh; i++)
+        for (int j = 0; j < kw; j++)
+            if (mask[i * kw + j]) {
+                k->dy[k->n] = (signed char)(i - ay); k->dx[k->n] = (signed char)(j - ax);
+                k->reach = std::max(k->reach, std::max(abs(i - ay), abs(j - ax)));
+                k->n++;
+            }
+    if (k->n == 0) { h->err = std::string(what) + ": structuring element has no non-zero entry"; return LFD_E_ARG; }
+    return LFD_OK;
+}
+
+// Arbitrary structuring elements for one pass (row-major uint8 masks, non-zero = member, anchor at the centre like
+// cv2.erode / cv2.dilate called with the default anchor: processfield.py:354, :464, :471).  erode_mask may be NULL.
+extern "C" int lfd_set_kernels(lfd_handle* h, int pass, const uint8_t* erode_mask, int eh, int ew,
+                               const uint8_t* dilate_mask, int dh, int dw)
+{
+    if (!h || (pass != 0 && pass != 1) || !dilate_mask) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (!h->have_params) { h->err = "lfd_set_params has not been called"; return LFD_E_STATE; }
+    CK(cudaStreamSynchronize(h->stream));
+    int rc;
+    if ((rc = fill_anykernel(h, &h->anyk_h[pass][0], pass == 1 ? erode_mask : nullptr, eh, ew, "erodeKernel")) != LFD_OK) return rc;
+    if ((rc = fill_anykernel(h, &h->anyk_h[pass][1], dilate_mask, dh, dw, "dilateKernel")) != LFD_OK) return rc;
+    CK(cudaMemcpy(h->anyk_d + pass * 2, &h->anyk_h[pass][0], 2 * sizeof(AnyKernel), cudaMemcpyHostToDevice));
+    h->anyk_on[pass] = true;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    static size_t anyk_max = 48 * 1024;
+    size_t need = anyk_smem(h->anyk_h[pass][0].reach, h->anyk_h[pass][1].reach);
+    if (need > anyk_max) { anyk_max = need; CK(cudaFuncSetAttribute(k_morph_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)anyk_max)); }
     return LFD_OK;
 }
 
@@ -605,6 +650,14 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         const int nunits = nstrips * nchunks;
         dim3 gg((nunits + 3) / 4, n);
         bool done = false;
+        if (h->anyk_on[pass]) {
+            const AnyKernel* ekd = (pass == 1 && h->anyk_h[pass][0].n > 0) ? h->anyk_d + pass * 2 : nullptr;
+            const AnyKernel* dkd = h->anyk_d + pass * 2 + 1;
+            const int re = ekd ? h->anyk_h[pass][0].reach : 0, rd = h->anyk_h[pass][1].reach;
+            dim3 ag((d.W + ANYK_TW - 1) / ANYK_TW, (d.H + ANYK_TH - 1) / ANYK_TH, n);
+            k_morph_any<<<ag, 256, anyk_smem(re, rd), s>>>(v_gray, lutp, v_morph, v_nz, etap, C, pass, d, ekd, dkd);
+            done = true;
+        }
 #define MORPH_CASE(EH_, EW_, DH_, DW_)                                                                              \
         if (!done && (d.W % 8) == 0 && mc.eh == EH_ && mc.ew == EW_ && mc.dh == DH_ && mc.dw == DW_) {                \
             k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(v_gray, lutp, v_morph, v_nz, etap, \

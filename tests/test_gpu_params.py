@@ -45,8 +45,21 @@ def _check(h, pass_, work, params, shape_tag):
     assert result_from_device(r, pass_, work.shape) == ref_res
 
 
+def _cross(n):
+    k = np.zeros((n, n), np.uint8); k[n // 2, :] = 1; k[:, n // 2] = 1
+    return k
+
+
+def _ellipse(h, w):
+    import cv2
+    return cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (w, h))
+
+
 PARAM_SETS = [
     # (bright overrides, dim overrides)
+    ({"dilateKernel": _cross(5)}, {"erodeKernel": _cross(3), "dilateKernel": _ellipse(9, 9)}),           # non-rectangular elements
+    ({"dilateKernel": _ones(27, 25)}, {"erodeKernel": _ones(5, 5), "dilateKernel": _ones(31, 31)}),          # rectangles beyond the tile halo
+    ({"dilateKernel": _ellipse(7, 4)}, {"erodeKernel": _ones(3, 3), "dilateKernel": (np.random.default_rng(5).random((11, 8)) < 0.4).astype(np.uint8) | _cross(11)[:, :8]}),
     ({"dilateKernel": _ones(9, 9)}, {"dilateKernel": _ones(15, 15)}),                                    # config 4: larger dilation
     ({"houghMethod": 5}, {"dilateKernel": _ones(15, 15), "houghMethod": 2}),                            # finer rho
     ({"dilateKernel": _ones(5, 3)}, {"erodeKernel": _ones(2, 2), "dilateKernel": _ones(6, 7)}),          # generic tile kernel

@@ -136,11 +136,14 @@ def test_result_decoding():
         result_from_device(r, 0, (1489, 2048))
 
 
-def test_unsupported_params_are_rejected():
+def test_kernel_shapes_are_passed_through():
     pb, pd, _ = lfd_b200.default_params()
-    bad = dict(pd, erodeKernel=np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8))
-    with pytest.raises(_lib.UnsupportedParameter):
-        _lib.pass_params(bad, True)
+    cross = dict(pd, erodeKernel=np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8))
+    p = _lib.pass_params(cross, True)              # a cross is legal: it goes to lfd_set_kernels at set_params time
+    assert (p.erode_h, p.erode_w, p.dilate_h, p.dilate_w) == (3, 3, 9, 9)
+    assert not _lib._all_ones(cross["erodeKernel"]) and _lib._all_ones(pd["dilateKernel"])
+    with pytest.raises(ValueError):
+        _lib.pass_params(dict(pd, dilateKernel=np.ones(5, np.uint8)), True)
 
 
 def test_check_theta_matches_oracle():
