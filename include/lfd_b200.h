@@ -98,7 +98,7 @@ typedef struct lfd_pass_params {
     double minFlux;             /* dim only */
     double addFlux;             /* dim only */
     int32_t nlinesInSet;        /* <= LFD_MAX_SET_LINES */
-    int32_t contoursMode;       /* cv2.RETR_*: LIST(1) and CCOMP(2), TREE(3) give the same set; EXTERNAL(0) unsupported */
+    int32_t contoursMode;       /* cv2.RETR_*: LIST(1), CCOMP(2), TREE(3) give the same contour set; EXTERNAL(0) = outermost outer borders only */
     int32_t contoursMethod;     /* cv2.CHAIN_APPROX_NONE(1) or SIMPLE(2) (same hulls); TC89_* unsupported */
     int32_t erode_h, erode_w;   /* 0,0 = no erosion (bright).  All-ones rectangles; other shapes: lfd_set_kernels. */
     int32_t dilate_h, dilate_w;
@@ -130,7 +130,7 @@ typedef struct lfd_result {
 /* a minimum-area rectangle as cv2.minAreaRect returns it (processfield.py:249) */
 typedef struct lfd_rect {
     float cx, cy, w, h, angle;
-    int32_t kind;               /* 0 = outer border of an edge component, 1 = hole border */
+    int32_t kind;               /* 0 = outer border of an edge component, 1 = hole border, 2 = not retrieved (RETR_EXTERNAL) */
     int32_t key;                /* raster-first pixel index (y*W+x) of the component / hole */
     int32_t passed;             /* 1 if it passed the length/width filter (processfield.py:256-257) */
     int32_t box[8];             /* int32(boxPoints(rect)) x0,y0..x3,y3 (processfield.py:259-260); valid if passed */

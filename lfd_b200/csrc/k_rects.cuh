@@ -368,7 +368,8 @@ __device__ __forceinline__ void rect_warp_path(const int* __restrict__ rmin, con
 __global__ void __launch_bounds__(RECT_WARPS * 32)
 k_rects_warp(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const CclBuf* __restrict__ ccl0,
              const CclBuf* __restrict__ ccl1, FrameCtl* __restrict__ ctl, int pass, int nframes,
-             Dims d, double minLen, double lwTresh, unsigned long long* __restrict__ counters)
+             Dims d, double minLen, double lwTresh, unsigned long long* __restrict__ counters,
+             const u32* __restrict__ edges, int external_only)
 {
     extern __shared__ u32 rsm[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -407,7 +408,32 @@ k_rects_warp(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const Ccl
             const CompBuf& cbr = comps[f];
             hh = cbr.h[e]; slot = cbr.slot[e]; ho = cbr.hulloff[e]; y0 = cbr.y0[e];
         }
-        bool small = valid && hh <= RECT_T_ROWS;
+        bool valid2 = valid;
+        if (valid && external_only) {
+            // cv2.RETR_EXTERNAL: only outer borders whose surrounding region is the outside of the image.  The region
+            // around an edge component is the background component of the pixel left of its raster-first pixel
+            // (Suzuki's border following starts there); "outside" = that component reaches the frame border (or the
+            // component itself starts in column 0).  Hole borders are never retrieved.
+            bool keep = false;
+            if (kind == 0) {
+                const CclBuf& fg = ccl0[f];
+                const CclBuf& bg = ccl1[f];
+                Run rr = fg.runs[comps[f].root[e]];
+                if (rr.xs == 0) keep = true;
+                else {
+                    int bid = run_at(edges + (size_t)f * d.NW, bg, rr.y, (int)rr.xs - 1, d, 1);
+                    keep = (bg.flag[bg.parent[bid]] & 1) != 0;
+                }
+            }
+            if (!keep) {
+                lfd_rect o;
+                memset(&o, 0, sizeof(o));
+                o.kind = 2;                      // not retrieved in this contoursMode
+                rbufs[f].rects[e] = o;
+                valid2 = false;
+            }
+        }
+        bool small = valid2 && hh <= RECT_T_ROWS;
         __syncwarp();
         // stage the row extremes of the 32 contours with coalesced loads: contour l -> column l of R
         u32* Rw = wsm + RECT_T_PTS * RECT_TPW;
@@ -430,7 +456,7 @@ k_rects_warp(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const Ccl
             if (!small) atomicAdd(&counters[12], 1ull);
             if (small) emit_rect(r, e, kind, f, pass, comps[f], rbufs[f], ccl0, ccl1, ctl, d, minLen, lwTresh);
         }
-        u32 big = __ballot_sync(FULLMASK, valid && !small);
+        u32 big = __ballot_sync(FULLMASK, valid2 && !small);
         if (lane == 0 && big) atomicAdd(&counters[11], (unsigned long long)__popc(big));
         while (big) {
             const int src = __ffs(big) - 1;

@@ -529,7 +529,6 @@ extern "C" int lfd_host_frames(lfd_handle* h, float** out)
 static int check_pass_params(lfd_handle* h, const lfd_pass_params& p, bool dim)
 {
     if (p.nlinesInSet < 1 || p.nlinesInSet > LFD_MAX_SET_LINES) { h->err = "nlinesInSet must be in 1..16"; return LFD_E_UNSUPPORTED; }
-    if (p.contoursMode == 0) { h->err = "contoursMode RETR_EXTERNAL is not implemented"; return LFD_E_UNSUPPORTED; }
     if (p.contoursMode < 0 || p.contoursMode > 3) { h->err = "unknown contoursMode"; return LFD_E_ARG; }
     if (p.contoursMethod != 1 && p.contoursMethod != 2) { h->err = "contoursMethod CHAIN_APPROX_TC89_* is not implemented"; return LFD_E_UNSUPPORTED; }
     if (p.dilate_h < 1 || p.dilate_w < 1) { h->err = "dilateKernel missing"; return LFD_E_ARG; }
@@ -714,7 +713,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 4);
     // rectangles + box image
-    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
+    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d, v_edges, pp.contoursMode == 0 ? 1 : 0); LAUNCH_CHECK();
     CK(cudaMemsetAsync(v_box, 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(v_rbuf, v_box, C, pass, d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 5);

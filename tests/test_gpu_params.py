@@ -32,6 +32,14 @@ def _check(h, pass_, work, params, shape_tag):
     if pass_ == 1 and "eroded" in taps and params.get("erodeKernel") is not None:
         if not np.array_equal(h.stage(0, pass_, "eroded"), taps["eroded"]):
             errs.append("eroded")
+    # the retrieved contour set: as many rectangles as cv2.findContours returned contours in this mode, same passing ones
+    rects = h.stage(0, pass_, "rects")
+    got_rects = [r for r in rects if r["kind"] != 2]
+    if len(got_rects) != len(taps["rects"]):
+        errs.append("contours: %d retrieved vs %d from cv2" % (len(got_rects), len(taps["rects"])))
+    gp = sorted(((float(a["cx"]), float(a["cy"])), (float(a["w"]), float(a["h"])), float(a["angle"])) for a in got_rects if a["passed"])
+    if gp != sorted(x for x, _ in taps["passing"]):
+        errs.append("passing rects differ: %d vs %d" % (len(gp), len(taps["passing"])))
     if taps["passing"]:
         for which, key in (("equ", "lines_equ"), ("box", "lines_box")):
             ref_lines = taps[key]
@@ -63,6 +71,8 @@ PARAM_SETS = [
     ({"dilateKernel": _ones(9, 9)}, {"dilateKernel": _ones(15, 15)}),                                    # config 4: larger dilation
     ({"houghMethod": 5}, {"dilateKernel": _ones(15, 15), "houghMethod": 2}),                            # finer rho
     ({"dilateKernel": _ones(5, 3)}, {"erodeKernel": _ones(2, 2), "dilateKernel": _ones(6, 7)}),          # generic tile kernel
+    ({"contoursMode": 0}, {"contoursMode": 0}),                                                          # cv2.RETR_EXTERNAL
+    ({"contoursMode": 0, "dilateKernel": _ones(9, 9), "lwTresh": 2}, {"contoursMode": 0, "contoursMethod": 2, "lwTresh": 3}),
     ({"dilateKernel": _ones(3, 3), "nlinesInSet": 5, "lwTresh": 3}, {"erodeKernel": _ones(3, 3), "dilateKernel": _ones(9, 9), "minFlux": 0.03, "addFlux": 1.5}),
 ]
 
