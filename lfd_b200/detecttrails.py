@@ -190,6 +190,8 @@ def compute_fields(frames, params_bright, params_dim, params_removestars, batch=
     from concurrent.futures import ThreadPoolExecutor
     debug = bool(params_bright["debug"] or params_dim["debug"])
     frames = list(frames)
+    if debug:
+        return _compute_fields_debug(frames, params_bright, params_dim, params_removestars)
     batch = max(int(batch), 1)
     chunks = [frames[i:i + batch] for i in range(0, len(frames), batch)]
     records = [None] * len(frames)
@@ -309,6 +311,30 @@ def compute_fields(frames, params_bright, params_dim, params_removestars, batch=
             records[g] = ("line", item[4] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n")
         else:
             records[g] = ("none", "")
+    return records
+
+
+def _compute_fields_debug(frames, params_bright, params_dim, params_removestars):
+    """debug=True: one frame at a time through the standalone stage functions, which write the reference's debug
+    images into $DEBUG_PATH and print the check_theta values (detecttrails.py:119-131 literally)."""
+    from .processfield import process_field_bright, process_field_dim
+    from .removestars import remove_stars
+    records = []
+    for (run, camcol, filter, field) in frames:
+        try:
+            img, printit = _load_frame(run, camcol, filter, field)
+            img = remove_stars(_np.ascontiguousarray(img, _np.float32), run, camcol, filter, field, **params_removestars)
+            img = _np.ascontiguousarray(img[::-1])                   # cv2.flip(img, 0)
+            detection, res = process_field_bright(img, **params_bright)
+            if not detection:
+                detection, res = process_field_dim(img, **params_dim)
+            if detection:
+                records.append(("line", printit + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n"))
+            else:
+                records.append(("none", ""))
+        except Exception as e:   # noqa: BLE001
+            traceback.print_exception(type(e), e, e.__traceback__, limit=3)
+            records.append(("err", _error_text(run, camcol, filter, field, e)))
     return records
 
 

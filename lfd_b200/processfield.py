@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["process_field_bright", "process_field_dim", "pathBright", "check_theta", "dictify_hough",
-           "fit_minAreaRect", "setup_debug"]
+           "fit_minAreaRect", "setup_debug", "draw_lines"]
 
 pathBright = None
 pathDim = None
@@ -68,19 +68,81 @@ def dictify_hough(shape, houghVals):
     return {"x1": x1, "y1": y1, "x2": x2, "y2": y2}
 
 
-def _dump_debug(handle, pass_, bright):
-    """The reference's debug PNG taps (processfield.py:349-378, :459-496), written as .npy arrays
-    (no image codec on this path)."""
+def _write_png(path, arr, compression=0):
+    """Minimal PNG encoder (8-bit gray or BGR colour arrays) so that the debug taps need no image library."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(arr, np.uint8)
+    if a.ndim == 3:
+        a = np.ascontiguousarray(a[:, :, ::-1])          # BGR (cv2 convention) -> RGB
+        ctype = 2
+    else:
+        ctype = 0
+    hgt, wid = a.shape[:2]
+    raw = np.concatenate([np.zeros((hgt, 1), np.uint8), a.reshape(hgt, -1)], axis=1).tobytes()    # filter byte 0 per row
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", wid, hgt, 8, ctype, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, int(compression))) + chunk(b"IEND", b""))
+
+
+def draw_lines(hough, image, nlines, name, path=None, compression=0, color=(255, 0, 0)):
+    """processfield.py:153-198: draw the first ``nlines`` Hough lines on a colour copy of ``image`` and save
+    ``<path>/<name>.png``.  Debug visualisation only (2-px lines rasterised with NumPy, not cv2.line's exact pixels)."""
+    path = pathDim if path is None else path
+    n_x, n_y = image.shape
+    draw = np.repeat(np.ascontiguousarray(image, np.uint8)[:, :, None], 3, axis=2)
+    for houghparams in (hough if hough is not None else [])[:nlines]:
+        try:
+            rho, theta = houghparams[0]
+            x0 = np.cos(theta) * rho
+            y0 = np.sin(theta) * rho
+            x1 = int(x0 - (n_x + n_y) * np.sin(theta)); y1 = int(y0 + (n_x + n_y) * np.cos(theta))
+            x2 = int(x0 + (n_x + n_y) * np.sin(theta)); y2 = int(y0 - (n_x + n_y) * np.cos(theta))
+            n = max(abs(x2 - x1), abs(y2 - y1)) + 1
+            t = np.linspace(0.0, 1.0, n)
+            xs = np.rint(x1 + (x2 - x1) * t).astype(np.int64)
+            ys = np.rint(y1 + (y2 - y1) * t).astype(np.int64)
+            for dx, dy in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                ok = (xs + dx >= 0) & (xs + dx < n_y) & (ys + dy >= 0) & (ys + dy < n_x)
+                draw[ys[ok] + dy, xs[ok] + dx] = color
+        except Exception:   # noqa: BLE001 - the reference ignores lines it cannot draw
+            pass
+    _write_png(os.path.join(path, name + ".png"), draw, compression)
+
+
+def _dump_debug(handle, pass_, bright, params):
+    """The reference's debug taps (processfield.py:349-378, :459-496): the same PNG file names in $DEBUG_PATH, and the
+    check_theta printout (:104-132) through the host mirror of that function."""
     path = pathBright if bright else pathDim
     if path is None:
         return
     names = ([("1equBRIGHT", "equ"), ("2dilateBRIGHT", "morph"), ("3contoursBRIGHT", "box")] if bright else
              [("6equDIM", "equ"), ("7erodedDIM", "eroded"), ("8openedDIM", "morph"), ("9contoursDIM", "box")])
+    imgs = {}
     for fname, stage in names:
         try:
-            np.save(os.path.join(path, fname + ".npy"), handle.stage(0, pass_, stage))
+            imgs[stage] = handle.stage(0, pass_, stage)
+            _write_png(os.path.join(path, fname + ".png"), imgs[stage])
         except _lib.LfdError:
             pass
+    try:
+        leq, lbox = handle.stage(0, pass_, "lines_equ"), handle.stage(0, pass_, "lines_box")
+    except _lib.LfdError:
+        return
+    if len(leq) and len(lbox) and "morph" in imgs and "box" in imgs:
+        nl = int(params["nlinesInSet"])
+        if bright:
+            draw_lines(lbox, imgs["box"], nl, "4boxhoughBRIGHT", path=path)
+            draw_lines(leq, imgs["morph"], nl, "5equhoughBRIGHT", path=path)
+        else:
+            draw_lines(leq, imgs["morph"], nl, "10equhoughDIM", path=path)
+            draw_lines(lbox, imgs["box"], nl, "11boxhoughDIM", path=path)
+        check_theta(leq, lbox, nl, params["dro"], params["thetaTresh"], params["lineSetTresh"], True)
 
 
 def result_from_device(r, pass_, shape):
@@ -113,11 +175,11 @@ def _run(pass_, img, params, dim):
         pb = params
     h.set_params(pb, pd)
     debug = bool(params.get("debug", False))
-    r = h.run_pass(pass_, work, flags=_lib.KEEP_TAPS if debug else 0, writeback=True)
+    r = h.run_pass(pass_, work, flags=(_lib.KEEP_TAPS | _lib.FULL_LINES) if debug else 0, writeback=True)
     if work is not img:
         img[...] = work      # the reference mutates its argument in place
     if debug:
-        _dump_debug(h, pass_, not dim)
+        _dump_debug(h, pass_, not dim, params)
     return result_from_device(r, pass_, img.shape)
 
 

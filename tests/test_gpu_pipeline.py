@@ -112,6 +112,20 @@ def test_detecttrails_dropin(tmp_path, cv2mod):
     # a second run with the same progress file has nothing left to do
     lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", savepath=str(out2), batch=4, resume=True).process()
     assert (out2 / "results.txt").read_text().splitlines() == rows
+    # debug=True: same result lines, plus the reference's debug images in $DEBUG_PATH (processfield.py:349-378, :459-496)
+    dbg = tmp_path / "dbg"
+    dbg.mkdir()
+    lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], str(dbg))
+    out3 = tmp_path / "out3"
+    out3.mkdir()
+    lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", savepath=str(out3), debug=True).process()
+    assert (out3 / "results.txt").read_text() == got
+    names = set(os.listdir(dbg))
+    assert {"1equBRIGHT.png", "2dilateBRIGHT.png", "3contoursBRIGHT.png", "6equDIM.png", "7erodedDIM.png", "8openedDIM.png",
+            "9contoursDIM.png"} <= names, names
+    assert names & {"5equhoughBRIGHT.png", "10equhoughDIM.png"}
+    png = cv2mod.imread(str(dbg / "2dilateBRIGHT.png"), 0)
+    assert png is not None and png.shape == (synth.FRAME_H, synth.FRAME_W)
     # missing frame -> errors.txt, processing continues (detecttrails.py:84-87, :133-139)
     dt2 = lfd_b200.DetectTrails(run=2888, camcol=1, filter="r", field=999, savepath=str(out))
     dt2.process()
