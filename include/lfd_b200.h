@@ -205,6 +205,12 @@ int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, uint8_t* edg
  * roofline the Hough vote kernel (shared-memory-privatised accumulators) is reported against. */
 int lfd_smem_atomic_peak(lfd_handle* h, double* gops);
 
+/* fit_minAreaRect(img, contoursMode, contoursMethod, minAreaRectMinLen, lwTresh) of processfield.py:201-263 on a host
+ * uint8 image of the handle's frame size: Canny(0,255) -> findContours -> minAreaRect filter -> fillPoly.
+ * box_out: uint8 height*width (0/255) = box_img; *detection = the function's first return value. */
+int lfd_fit_min_area_rect(lfd_handle* h, const uint8_t* img, int contoursMode, int contoursMethod,
+                          double minAreaRectMinLen, double lwTresh, uint8_t* box_out, int* detection);
+
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
 const char* lfd_timing_name(int i);

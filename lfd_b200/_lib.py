@@ -118,6 +118,8 @@ def lib():
                                       ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
         L.lfd_canny.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.lfd_smem_atomic_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        L.lfd_fit_min_area_rect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                            ctypes.c_double, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -345,6 +347,18 @@ class Handle:
         g = ctypes.c_double()
         self._ck(self._L.lfd_smem_atomic_peak(self.h, ctypes.byref(g)))
         return float(g.value)
+
+    def fit_min_area_rect(self, img, contoursMode, contoursMethod, minAreaRectMinLen, lwTresh):
+        """(detection, box_img) of processfield.py:201-263 for a uint8 image of this handle's frame size."""
+        img = np.ascontiguousarray(img, np.uint8)
+        if img.shape != (self.H, self.W):
+            raise ValueError("image shape must be (%d, %d)" % (self.H, self.W))
+        out = np.empty((self.H, self.W), np.uint8)
+        det = ctypes.c_int()
+        self._ck(self._L.lfd_fit_min_area_rect(self.h, img.ctypes.data_as(ctypes.c_void_p), int(contoursMode), int(contoursMethod),
+                                               float(minAreaRectMinLen), float(lwTresh), out.ctypes.data_as(ctypes.c_void_p),
+                                               ctypes.byref(det)))
+        return bool(det.value), out
 
     def timings(self):
         ms = (ctypes.c_float * 32)()

@@ -607,7 +607,8 @@ extern "C" int lfd_set_kernels(lfd_handle* h, int pass, const uint8_t* erode_mas
 // the pipeline
 // ------------------------------------------------------------------------------------------------
 // frames [f0, f0 + n) of the batch: every per-frame array is entered at frame f0, kernels index frames from 0
-static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, cudaStream_t s, bool stage_events)
+// `part`: 0 = the whole pass ; 1 = only the contour part (NMS .. box fill) on a morph plane + nz mask the caller put in place
+static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, cudaStream_t s, bool stage_events, int part = 0)
 {
 #define STAGE_EVENT(i) do { if (stage_events) CK(cudaEventRecord(h->ev[i], s)); } while (0)
     const Dims d = h->d;
@@ -634,6 +635,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
+    if (part == 0) {
     // LUT + morphology
     k_lut<<<dim3(n, 1), 256, 0, s>>>(h->hist + (size_t)f0 * 256, h->lut + (size_t)f0 * 256, C, h->B, d.N, pass); LAUNCH_CHECK();
     MorphCfg mc;
@@ -676,6 +678,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         LAUNCH_CHECK();
     }
     STAGE_EVENT(tbase + 1);
+    }
     // Sobel + NMS
     u8* ntap = nullptr;
     if (taps) {
@@ -717,6 +720,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     CK(cudaMemsetAsync(v_box, 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(v_rbuf, v_box, C, pass, d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 5);
+    if (part == 1) return LFD_OK;
     // Hough on the morphology output and on the box image
     int* const v_accum = hb.accum + (size_t)f0 * 2 * hb.accum_stride;
     u64* const v_keys = hb.keys + (size_t)f0 * 2 * hb.key_stride;
@@ -1160,6 +1164,44 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     CK(cudaStreamSynchronize(s));
     if (out.status & LFD_FRAME_OVERFLOW) { h->err = "edge map has more runs than lfd_config.max_runs"; return LFD_E_CAPACITY; }
     return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone fit_minAreaRect (processfield.py:201-263): Canny -> contours -> minAreaRect filter -> box image
+// ------------------------------------------------------------------------------------------------
+extern "C" int lfd_fit_min_area_rect(lfd_handle* h, const uint8_t* img, int contoursMode, int contoursMethod,
+                                     double minAreaRectMinLen, double lwTresh, uint8_t* box_out, int* detection)
+{
+    if (!h || !img || !box_out || !detection) { if (h) h->err = "bad argument"; return LFD_E_ARG; }
+    cudaSetDevice(h->device);
+    if (h->pending) { h->err = "previous batch not collected (call lfd_wait)"; return LFD_E_STATE; }
+    if (!h->have_params) { h->err = "lfd_set_params has not been called"; return LFD_E_STATE; }
+    if (contoursMode < 0 || contoursMode > 3) { h->err = "unknown contoursMode"; return LFD_E_ARG; }
+    if (contoursMethod != 1 && contoursMethod != 2) { h->err = "contoursMethod CHAIN_APPROX_TC89_* is not implemented"; return LFD_E_UNSUPPORTED; }
+    const Dims d = h->d;
+    cudaStream_t s = h->stream;
+    const lfd_pass_params saved = h->params.bright;
+    h->params.bright.contoursMode = contoursMode; h->params.bright.contoursMethod = contoursMethod;
+    h->params.bright.minAreaRectMinLen = minAreaRectMinLen; h->params.bright.lwTresh = lwTresh;
+    int rc = LFD_OK;
+    do {
+        cudaError_t ce;
+        if ((ce = cudaMemcpyAsync(h->morph[0], img, (size_t)d.N, cudaMemcpyHostToDevice, s)) != cudaSuccess) { h->err = cudaGetErrorString(ce); rc = LFD_E_CUDA; break; }
+        k_ctl_init<<<1, 32, 0, s>>>(h->ctl, h->B, h->res_d, 1, 1, 0);
+        k_pack_mask<<<592, 256, 0, s>>>(h->morph[0], h->nz[0], d);
+        h->launches += 2;
+        if ((rc = run_pass_kernels(h, 0, 1, 0, 0, s, false, 1)) != LFD_OK) break;
+        k_expand_mask<<<dim3(592, 1), 256, 0, s>>>(h->box[0], h->tap_u8, d);
+        h->launches++;
+        FrameCtl out;
+        if ((ce = cudaMemcpyAsync(&out, h->ctl, sizeof(out), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (ce = cudaMemcpyAsync(box_out, h->tap_u8, (size_t)d.N, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (ce = cudaStreamSynchronize(s)) != cudaSuccess) { h->err = cudaGetErrorString(ce); rc = LFD_E_CUDA; break; }
+        if (out.status & LFD_FRAME_OVERFLOW) { h->err = "per-frame work list overflow (lfd_config.max_runs / max_components)"; rc = LFD_E_CAPACITY; break; }
+        *detection = out.hough[0] ? 1 : 0;
+    } while (0);
+    h->params.bright = saved;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -203,8 +203,16 @@ def process_field_dim(img, minFlux, addFlux, lwTresh, thetaTresh, erodeKernel, d
 
 
 def fit_minAreaRect(img, contoursMode, contoursMethod, minAreaRectMinLen, lwTresh, debug):
-    """processfield.py:201-263 is not separately exported by the reference (``__all__``); the GPU
-    library runs it inside a pass.  Provided for completeness through a bright pass with a 1x1 dilation
-    on an image that is already uint8-valued."""
-    raise NotImplementedError("fit_minAreaRect runs inside process_field_bright/dim; use the stage taps "
-                              "(lfd_b200._lib.Handle.stage(..., 'box')) to read box_img")
+    """processfield.py:201-263 on the GPU: ``(detection, box_img)`` for a uint8 image (Canny(0,255) -> findContours ->
+    minAreaRect filter -> fillPoly of the int-truncated boxPoints)."""
+    if not isinstance(img, np.ndarray) or img.ndim != 2:
+        raise TypeError("img must be a 2-D numpy array")
+    h = _lib.default_handle(img.shape[0], img.shape[1])
+    if h._params_key is None:
+        from .detecttrails import default_params
+        pb, pd, _ = default_params()
+        h.set_params(pb, pd)
+    detection, box_img = h.fit_min_area_rect(img, contoursMode, contoursMethod, minAreaRectMinLen, lwTresh)
+    if debug and pathBright is not None:
+        _write_png(os.path.join(pathBright, "3contours.png"), box_img)
+    return detection, box_img

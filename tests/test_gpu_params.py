@@ -201,3 +201,16 @@ def test_config5_microbench_hough_canny(cv2mod):
             assert np.array_equal(got, ref), (sigma, lo, hi, int((got != ref).sum()))
     finally:
         h.close()
+
+
+def test_fit_min_area_rect_standalone(cv2mod):
+    """lfd_b200.processfield.fit_minAreaRect == the reference's fit_minAreaRect (processfield.py:201-263) on uint8 images."""
+    from lfd_b200.processfield import fit_minAreaRect
+    img, _ = synth.make_case("dense_trail", 91)
+    taps = {}
+    rp.bright_pass(np.ascontiguousarray(img[::-1]).copy(), taps=taps, **rp.DEFAULT_BRIGHT)
+    equ = taps["morph"]
+    for mode, method, minlen, lw in ((1, 1, 1, 5), (0, 2, 1, 3), (2, 1, 3, 2)):
+        ref_det, ref_box = rp.fit_rects(equ, mode, method, minlen, lw)
+        det, box = fit_minAreaRect(equ, mode, method, minlen, lw, False)
+        assert det == ref_det and np.array_equal(box, ref_box), (mode, method, minlen, lw)
