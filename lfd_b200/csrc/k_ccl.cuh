@@ -635,6 +635,127 @@ k_ccl_extremes(const u32* __restrict__ edges, CclBuf* __restrict__ bufs, CompBuf
     }
 }
 
+// ---- flat (one thread per run) variants of steps 5-8 ---------------------------------------------------
+// A frame has ~10-40 runs per row, so a warp-per-row grid leaves most lanes idle and launches ~1500 warps per
+// frame that each wait on the same chain of dependent loads.  Runs are stored contiguously per frame
+// (id = raster order), so these kernels simply stride over [0, nruns): full warps, 3x fewer of them.
+#define CCL_FLAT_CTAS 48          // CTAs of 256 threads per frame (grid-stride over the frame's runs)
+
+__global__ void __launch_bounds__(256)
+k_ccl_stats_flat(const u32* __restrict__ strong, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
+                 int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    const int nruns = ctl[f].nruns[kind];
+    CclBuf b = bufs[f];
+    const u32* sm = strong ? strong + (size_t)f * d.NW : nullptr;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < nruns; id += gridDim.x * blockDim.x) {
+        Run r = b.runs[id];
+        const int y = r.y;
+        int root = uf_find_ro(b.parent, id);
+        b.parent[id] = root;
+        int fl = 0;
+        if (kind == 0) {
+            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                if (sm[(size_t)y * d.WW + w] & bit_range(blo, bhi)) { fl = 1; break; }
+            }
+        } else {
+            fl = (y == 0 || y == d.H - 1 || r.xs == 0 || r.xe == d.W - 1) ? 1 : 0;
+        }
+        if (fl) atomicOr(&b.flag[root], 1);
+        if (root != id) atomicMax(&b.ymax[root], y);
+    }
+}
+
+// fg: edge mask (pre-zeroed by the caller) + contour allocation ; bg: contour allocation only (edges == nullptr)
+__global__ void __launch_bounds__(256)
+k_ccl_alloc_flat(CclBuf* __restrict__ bufs, u32* __restrict__ edges, CompBuf* __restrict__ comps, FrameCtl* __restrict__ ctl,
+                 int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    const int nruns = ctl[f].nruns[kind];
+    CclBuf b = bufs[f];
+    CompBuf cb = comps[f];
+    u32* em = edges ? edges + (size_t)f * d.NW : nullptr;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < nruns; id += gridDim.x * blockDim.x) {
+        const int root = b.parent[id];
+        const int fl = b.flag[root] & 1;
+        const bool sel = kind == 0 ? fl : !fl;          // fg: holds a strong pixel ; bg: does not touch the border
+        if (!sel) continue;
+        Run r = b.runs[id];
+        const int y = r.y;
+        if (kind == 0) {
+            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                atomicOr(&em[(size_t)y * d.WW + w], bit_range(blo, bhi));
+            }
+        }
+        if (root != id) continue;
+        int ci = atomicAdd(&ctl[f].ncomp[kind], 1);
+        int hh = b.ymax[id] - y + 1 + (kind ? 2 : 0);
+        int slot = atomicAdd(&ctl[f].nslots[0], hh);
+        int ho = atomicAdd(&ctl[f].nhull[0], 2 * hh + 2);
+        if (ci >= cb.maxcomp || slot + hh > cb.slotcap || ho + 2 * hh + 2 > cb.hullcap) {
+            atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
+            continue;
+        }
+        int e = kind * cb.maxcomp + ci;
+        cb.root[e] = id;
+        cb.y0[e] = y - (kind ? 1 : 0);
+        cb.h[e] = hh;
+        cb.slot[e] = slot;
+        cb.hulloff[e] = ho;
+        for (int i = 0; i < hh; i++) { cb.rowmin[slot + i] = 0x7fffffff; cb.rowmax[slot + i] = -1; }
+        b.compidx[id] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_extremes_flat(const u32* __restrict__ edges, CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps,
+                    const FrameCtl* __restrict__ ctl, int pass, Dims d, int kind)
+{
+    int f = blockIdx.y;
+    if (!ctl[f].active[pass]) return;
+    const int nruns = ctl[f].nruns[kind];
+    CclBuf b = bufs[f];
+    CompBuf cb = comps[f];
+    const u32* em = edges + (size_t)f * d.NW;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < nruns; id += gridDim.x * blockDim.x) {
+        int e = b.compidx[b.parent[id]];
+        if (e < 0) continue;
+        Run r = b.runs[id];
+        const int y = r.y;
+        int s = cb.slot[e] + (y - cb.y0[e]);
+        if (kind == 0) {
+            atomicMin(&cb.rowmin[s], (int)r.xs);
+            atomicMax(&cb.rowmax[s], (int)r.xe);
+        } else {
+            // hole run [xs, xe] on row y (never on the frame border): edge pixels 4-adjacent to it
+            atomicMin(&cb.rowmin[s], (int)r.xs - 1);
+            atomicMax(&cb.rowmax[s], (int)r.xe + 1);
+            for (int dy = -1; dy <= 1; dy += 2) {
+                int yy = y + dy;
+                int first = -1, last = -1;
+                for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
+                    int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
+                    u32 bits = em[(size_t)yy * d.WW + w] & bit_range(blo, bhi);
+                    if (bits) {
+                        if (first < 0) first = (w << 5) + __ffs(bits) - 1;
+                        last = (w << 5) + 31 - __clz(bits);
+                    }
+                }
+                if (first >= 0) {
+                    atomicMin(&cb.rowmin[s + dy], first);
+                    atomicMax(&cb.rowmax[s + dy], last);
+                }
+            }
+        }
+    }
+}
+
 // labels tap: int32 per pixel = raster-first pixel index of the component (fg) / hole (bg)
 __global__ void __launch_bounds__(CCL_WARPS * 32)
 k_ccl_labels(CclBuf* __restrict__ bufs, int* __restrict__ labels, const FrameCtl* __restrict__ ctl, int pass,

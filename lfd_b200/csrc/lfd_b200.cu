@@ -702,18 +702,20 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl0, C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(v_strong, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_edges_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(v_ccl0, v_edges, v_comp, C, pass, d); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl0, v_comp, C, pass, d, 0); LAUNCH_CHECK();
+    const dim3 flat(CCL_FLAT_CTAS, n);
+    CK(cudaMemsetAsync(v_edges, 0, (size_t)n * d.NW * sizeof(u32), s));
+    k_ccl_stats_flat<<<flat, 256, 0, s>>>(v_strong, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_alloc_flat<<<flat, 256, 0, s>>>(v_ccl0, v_edges, v_comp, C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_extremes_flat<<<flat, 256, 0, s>>>(v_edges, v_ccl0, v_comp, C, pass, d, 0); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 3);
     // background runs: hole contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl1, C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(nullptr, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_alloc<<<rows, CCL_WARPS * 32, 0, s>>>(v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
-    k_ccl_extremes<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_stats_flat<<<flat, 256, 0, s>>>(nullptr, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_alloc_flat<<<flat, 256, 0, s>>>(v_ccl1, nullptr, v_comp, C, pass, d, 1); LAUNCH_CHECK();
+    k_ccl_extremes_flat<<<flat, 256, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 4);
     // rectangles + box image
     k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d, v_edges, pp.contoursMode == 0 ? 1 : 0); LAUNCH_CHECK();
