@@ -292,7 +292,7 @@ __device__ __forceinline__ void suf_union(int* p, int a, int b)
     }
 }
 
-#define CCL_BAND_CAP 2560          // runs of one band kept in shared memory (12 B each = 30 KB)
+#define CCL_BAND_CAP 1536          // runs of one band kept in shared memory (12 B each = 18 KB)
 
 // dynamic shared memory of k_ccl_band: CCL_BAND rows of mask words, then the band's parents and runs
 __host__ __device__ inline size_t ccl_band_smem(int WW) { return (size_t)CCL_BAND * WW * 4 + (size_t)CCL_BAND_CAP * 12; }
