@@ -284,10 +284,16 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                 const u32 bal = __ballot_sync(FULLMASK, nzf[sa]);
                 u32 myc = 0, mys = 0;                                // lane g keeps mask word g
                 const u16* Mu = sM[wid][sc]; const u16* Mc = sM[wid][sa]; const u16* Md = sM[wid][sb];
+                // bit 4*gi of gm: some pixel of 32-px group gi has a gradient (its four lanes 2+4gi .. 5+4gi)
+                u32 gm = bal >> 2;
+                gm = (gm | (gm >> 1) | (gm >> 2) | (gm >> 3)) & 0x1111111u;
+                if (TAP) gm = 0x1111111u;                            // the tap writes every pixel of the row
 #pragma unroll 1
-                for (int gi = 0; gi < 7; gi++) {
+                while (gm) {
+                    const int gi = (__ffs(gm) - 1) >> 2;
+                    gm &= gm - 1;
                     int cls = 0;
-                    if ((bal >> (2 + 4 * gi)) & 0xfu) {              // some pixel of this 32-px group has a gradient
+                    if ((bal >> (2 + 4 * gi)) & 0xfu) {              // (always true unless TAP)
                         const int x = 16 + 32 * gi + lane;           // pixel index inside the 256-px strip
                         const int mm = Mc[x];
                         if (mm > low) {
