@@ -214,3 +214,33 @@ def test_fit_min_area_rect_standalone(cv2mod):
         ref_det, ref_box = rp.fit_rects(equ, mode, method, minlen, lw)
         det, box = fit_minAreaRect(equ, mode, method, minlen, lw, False)
         assert det == ref_det and np.array_equal(box, ref_box), (mode, method, minlen, lw)
+
+
+def test_capacity_overflow_is_reported_not_silent(cv2mod):
+    """A frame with more runs / contours than the configured capacity comes back flagged (LFD_FRAME_OVERFLOW) instead of
+    with a wrong verdict; its batch neighbours are unaffected."""
+    from lfd_b200 import _lib
+    from lfd_b200.processfield import result_from_device
+    dense, _ = synth.make_case("dense", 6)
+    sparse, cat = synth.make_case("trail", 1234)
+    pb, pd = dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM)
+    h = _lib.Handle(synth.FRAME_H, synth.FRAME_W, max_batch=2, max_runs=20000, max_components=2000)
+    try:
+        h.set_params(pb, pd)
+        h.submit(np.stack([dense, sparse]), [np.zeros((0, 4), np.int32)] * 2)
+        r = h.wait()
+        assert r[0].status & _lib.FRAME_OVERFLOW
+        with pytest.raises(_lib.LfdError):
+            result_from_device(r[0], 0, dense.shape)
+        assert not (r[1].status & _lib.FRAME_OVERFLOW)
+        ref = rp.process_frame(sparse.copy(), {k: v[:0] for k, v in cat.items()}, "r")
+        got = (False, -1, None)
+        for p in (0, 1):
+            if r[1].rect_detection[p] >= 0:
+                d_, o_ = result_from_device(r[1], p, sparse.shape)
+                if d_:
+                    got = (True, p, o_)
+                    break
+        assert got == ref
+    finally:
+        h.close()
