@@ -128,7 +128,7 @@ k_canny_nms(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
 // ================================================================================================
 #include "k_morph.cuh"
 
-#define NMS_R 64
+#define NMS_R 32
 
 __device__ __forceinline__ u32 vneg2(u32 a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ u32 vsub2(u32 a, u32 b) { return __vadd2(a, vneg2(b)); }
