@@ -293,13 +293,23 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 
     // software pipeline: the U rows of the next block are requested before the current block is processed,
     // so the dependent min/max chain never waits on a global load (the kernel is latency-, not bandwidth-bound)
+    // Pixels outside the frame are "ignored" by cv2: they enter as the identity of the FIRST filter (255 for the
+    // erosion, 0 for the dilation) already at load time, so the row body has no special cases.  Row addresses are
+    // running element offsets (one 64-bit add per row instead of a 64-bit multiply chain per access).
+    const u32 identw = HAS_E ? 0xffffffffu : 0u;
+    const long long rstep = Ww >> 1;                           // uint2 elements per image row
+    long long ld_off = ((long long)yfirst * Ww + wx) >> 1;     // arithmetic shift: also right for rows above the frame
     uint2 nxt[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int y = yfirst + u;
-        nxt[u] = make_uint2(0u, 0u);
-        if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + (((size_t)y * Ww + wx) >> 1));
+        nxt[u] = make_uint2(identw, identw);
+        if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + ld_off);
+        ld_off += rstep;
     }
+    long long st_off = ((long long)y0 * Ww + wx) >> 1;          // output rows are produced in order y0, y0+1, ...
+    long long et_off = st_off;
+    int nz_off = f * d.NW + y0 * d.WW + mw;
     for (int yb = yfirst; yb <= ylast; yb += U) {
         uint2 cur[U];
 #pragma unroll
@@ -308,22 +318,18 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int y = yb + U + u;
-                nxt[u] = make_uint2(0u, 0u);
-                if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + (((size_t)y * Ww + wx) >> 1));
+                nxt[u] = make_uint2(identw, identw);
+                if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + ld_off);
+                ld_off += rstep;
             }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int y = yb + u;
             const uint2 v = cur[u];
-            const bool rin = y >= 0 && y < d.H;
             u32 p[4];
-            if (HAS_E && !(rin && col_in)) {
-                p[0] = p[1] = p[2] = p[3] = 0xffffffffu;
-            } else {
-                p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
-                p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
-            }
+            p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
+            p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
             u32 e[4];
             int ye = y;
             if (HAS_E) {
@@ -338,7 +344,8 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
                 if (et && ye >= y0 && ye < y1) {
                     u32 w0, w1;
                     lut_pack(e, slut, w0, w1);
-                    if (lane_out) et[((size_t)ye * Ww + wx) >> 1] = make_uint2(w0, w1);
+                    if (lane_out) et[et_off] = make_uint2(w0, w1);
+                    et_off += rstep;
                 }
             } else {
 #pragma unroll
@@ -357,14 +364,16 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
                 const bool anynz = __any_sync(FULLMASK, (o[0] | o[1] | o[2] | o[3]) != 0u);
                 if (anynz || lut0 != 0u) lut_pack(o, slut, w0, w1);
                 if (!lane_out) { w0 = 0; w1 = 0; }
-                if (lane_out) mo[((size_t)yo * Ww + wx) >> 1] = make_uint2(w0, w1);
+                if (lane_out) mo[st_off] = make_uint2(w0, w1);
+                st_off += rstep;
                 u32 bits = 0;
                 if (anynz || lut0 != 0u) {
                     bits = (nzbits4(w0) | (nzbits4(w1) << 4)) << q8;
                     bits |= __shfl_sync(FULLMASK, bits, src1);
                     bits |= __shfl_sync(FULLMASK, bits, src2);
                 }
-                if ((r & 3) == 0 && lane >= 2 && lane < 30 && mw < d.WW) nz[(size_t)f * d.NW + (size_t)yo * d.WW + mw] = bits;
+                if ((r & 3) == 0 && lane >= 2 && lane < 30 && mw < d.WW) nz[nz_off] = bits;
+                nz_off += d.WW;
             }
         }
     }
