@@ -201,7 +201,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
     const int wxc = min(max(wx, 0), Ww - 2);
     auto load_row = [&](int yi) -> uint2 {
         const int yl = min(max(yi, 0), d.H - 1);                     // BORDER_REPLICATE rows
-        return __ldg(g + (((size_t)yl * Ww + wxc) >> 1));
+        return __ldg(g + ((yl * Ww + wxc) >> 1));         // per-frame offsets fit 32 bits (H * W <= 2^28)
     };
     auto fix_row = [&](uint2 v) -> uint2 {
         if (!col_in) {                                               // BORDER_REPLICATE columns
@@ -237,7 +237,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                 __syncwarp();
                 if (yn >= y0 && yn < y1) {
                     if (!nzf_any[sa]) {
-                        if (lane < nwords) { candf[(size_t)yn * d.WW + mw0 + lane] = 0u; strongf[(size_t)yn * d.WW + mw0 + lane] = 0u; }
+                        if (lane < nwords) { const int o = yn * d.WW + mw0 + lane; candf[o] = 0u; strongf[o] = 0u; }
                         if (TAP)
                             for (int x = lane; x < 32 * nwords; x += 32)
                                 if (32 * mw0 + x < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + 32 * mw0 + x] = 0;
@@ -320,7 +320,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                         if (gi < nwords && xg < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + xg] = (u8)cls;
                     }
                 }
-                if (lane < nwords) { candf[(size_t)yn * d.WW + mw0 + lane] = myc; strongf[(size_t)yn * d.WW + mw0 + lane] = mys; }
+                if (lane < nwords) { const int o = yn * d.WW + mw0 + lane; candf[o] = myc; strongf[o] = mys; }
             }
             __syncwarp();
         }
