@@ -152,51 +152,6 @@ k_ccl_rowscan(CclBuf* __restrict__ bufs, FrameCtl* __restrict__ ctl, int pass, D
     }
 }
 
-// 3. materialise runs: id = rowbase[y] + rank; parent = id
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_fill(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
-           int pass, Dims d, int kind)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
-    if (y >= d.H) return;
-    const u32* m = mask + (size_t)f * d.NW;
-    CclBuf b = bufs[f];
-    int rb = b.rowbase[y];
-    for (int w = lane_id(); w < d.WW; w += 32) {
-        u32 cur = ccl_word(m, y, w, d, kind), prev = ccl_word(m, y, w - 1, d, kind);
-        u32 starts = cur & ~((cur << 1) | (prev >> 31));
-        int id = rb + b.wpre[(size_t)y * d.WW + w];
-        while (starts) {
-            int s = __ffs(starts) - 1;
-            starts &= starts - 1;
-            // end of the run: count the consecutive set bits from s upward (may continue in later words)
-            u32 above = ~(cur >> s);
-            int t = above ? (__ffs(above) - 1) : 32;       // s == 0 and an all-ones word
-            int xe;
-            if (s + t < 32) {
-                xe = (w << 5) + s + t - 1;
-            } else {
-                xe = (w << 5) + 31;
-                for (int w2 = w + 1; w2 < d.WW; w2++) {
-                    u32 nx = ~ccl_word(m, y, w2, d, kind);
-                    int t2 = nx ? (__ffs(nx) - 1) : 32;    // trailing ones of the next word
-                    xe = (w2 << 5) + t2 - 1;
-                    if (t2 < 32) break;
-                }
-            }
-            Run r; r.xs = (u16)((w << 5) + s); r.xe = (u16)xe; r.y = (u16)y; r.pad = 0;
-            b.runs[id] = r;
-            b.parent[id] = id;
-            b.flag[id] = 0;
-            b.ymax[id] = y;
-            b.compidx[id] = -1;
-            id++;
-        }
-    }
-}
-
 // index of the run of row y that contains pixel p (which must be set)
 __device__ __forceinline__ int run_at(const u32* __restrict__ m, const CclBuf& b, int y, int p, Dims d, int kind)
 {
@@ -241,28 +196,6 @@ __device__ __forceinline__ void link_rows(const u32* __restrict__ m, const CclBu
 }
 
 #define CCL_BAND 32
-
-// 4a. band-local merge: one CTA walks the rows of a CCL_BAND-row band in order and flattens each row
-//     right after linking it, so union-find trees inside a band never get deeper than a couple of hops
-//     (a frame-wide background component would otherwise build chains as long as the frame is tall).
-__global__ void __launch_bounds__(256)
-k_ccl_merge_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
-                 int pass, Dims d, int kind)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    if (ctl[f].nruns[kind] == 0) return;
-    const u32* m = mask + (size_t)f * d.NW;
-    CclBuf b = bufs[f];
-    int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
-    for (int y = y0 + 1; y < y1; y++) {
-        link_rows(m, b, y, d, kind, threadIdx.x, blockDim.x);
-        __syncthreads();
-        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-        for (int id = r0 + threadIdx.x; id < r1; id += blockDim.x) b.parent[id] = uf_find(b.parent, id);
-        __syncthreads();
-    }
-}
 
 // ---- shared-memory union-find (band-local): same algorithm as uf_find / uf_union on a __shared__ array
 __device__ __forceinline__ int suf_find(volatile int* p, int i)
@@ -433,66 +366,6 @@ k_ccl_merge(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const Frame
     link_rows(m, b, y, d, kind, lane_id(), 32);
 }
 
-// 5. flatten + per-component statistics at the root
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_stats(const u32* __restrict__ strong, CclBuf* __restrict__ bufs, const FrameCtl* __restrict__ ctl,
-            int pass, Dims d, int kind)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
-    if (y >= d.H) return;
-    CclBuf b = bufs[f];
-    if (ctl[f].nruns[kind] == 0) return;
-    const u32* sm = strong ? strong + (size_t)f * d.NW : nullptr;
-    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-    for (int id = r0 + lane_id(); id < r1; id += 32) {
-        Run r = b.runs[id];
-        int root = uf_find_ro(b.parent, id);
-        b.parent[id] = root;
-        int fl = 0;
-        if (kind == 0) {
-            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
-                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
-                if (sm[(size_t)y * d.WW + w] & bit_range(blo, bhi)) { fl = 1; break; }
-            }
-        } else {
-            fl = (y == 0 || y == d.H - 1 || r.xs == 0 || r.xe == d.W - 1) ? 1 : 0;
-        }
-        if (fl) atomicOr(&b.flag[root], 1);
-        if (root != id) atomicMax(&b.ymax[root], y);
-    }
-}
-
-// 6. Canny output: edges = runs of candidate components that hold a strong pixel
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_edges(CclBuf* __restrict__ bufs, u32* __restrict__ edges, const FrameCtl* __restrict__ ctl, int pass, Dims d)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int wid = threadIdx.x >> 5;
-    int y = blockIdx.x * CCL_WARPS + wid;
-    __shared__ u32 row[CCL_WARPS][128];
-    if (y >= d.H) return;
-    CclBuf b = bufs[f];
-    for (int w = lane_id(); w < d.WW; w += 32) row[wid][w] = 0;
-    __syncwarp();
-    if (ctl[f].nruns[0] > 0) {
-        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-        for (int id = r0 + lane_id(); id < r1; id += 32) {
-            int root = b.parent[id];
-            if (!(b.flag[root] & 1)) continue;
-            Run r = b.runs[id];
-            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
-                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
-                atomicOr(&row[wid][w], bit_range(blo, bhi));
-            }
-        }
-    }
-    __syncwarp();
-    for (int w = lane_id(); w < d.WW; w += 32) edges[(size_t)f * d.NW + (size_t)y * d.WW + w] = row[wid][w];
-}
-
 // Contour bookkeeping, one entry per selected component.
 struct CompBuf {
     int* root;        // [2*maxcomp]  fg entries first, then bg
@@ -505,137 +378,7 @@ struct CompBuf {
     int slotcap, hullcap, maxcomp;
 };
 
-// 7. allocate a contour for every selected root (fg: holds a strong pixel; bg: does not touch the border)
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_alloc(CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps, FrameCtl* __restrict__ ctl, int pass, Dims d, int kind)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
-    if (y >= d.H) return;
-    CclBuf b = bufs[f];
-    CompBuf cb = comps[f];
-    if (ctl[f].nruns[kind] == 0) return;
-    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-    for (int id = r0 + lane_id(); id < r1; id += 32) {
-        if (b.parent[id] != id) continue;
-        bool sel = kind == 0 ? (b.flag[id] & 1) : !(b.flag[id] & 1);
-        if (!sel) continue;
-        int ci = atomicAdd(&ctl[f].ncomp[kind], 1);
-        int hh = b.ymax[id] - y + 1 + (kind ? 2 : 0);
-        int slot = atomicAdd(&ctl[f].nslots[0], hh);
-        int ho = atomicAdd(&ctl[f].nhull[0], 2 * hh + 2);
-        if (ci >= cb.maxcomp || slot + hh > cb.slotcap || ho + 2 * hh + 2 > cb.hullcap) {
-            atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
-            continue;
-        }
-        int e = kind * cb.maxcomp + ci;
-        cb.root[e] = id;
-        cb.y0[e] = y - (kind ? 1 : 0);
-        cb.h[e] = hh;
-        cb.slot[e] = slot;
-        cb.hulloff[e] = ho;
-        for (int i = 0; i < hh; i++) { cb.rowmin[slot + i] = 0x7fffffff; cb.rowmax[slot + i] = -1; }
-        b.compidx[id] = e;
-    }
-}
-
-// 6+7 fused for the foreground pass (same grid, same runs): write the Canny edge mask of the row and allocate
-// the contours whose root run lies on it.
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_edges_alloc(CclBuf* __restrict__ bufs, u32* __restrict__ edges, CompBuf* __restrict__ comps, FrameCtl* __restrict__ ctl,
-                  int pass, Dims d)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int wid = threadIdx.x >> 5;
-    int y = blockIdx.x * CCL_WARPS + wid;
-    __shared__ u32 row[CCL_WARPS][128];
-    if (y >= d.H) return;
-    CclBuf b = bufs[f];
-    CompBuf cb = comps[f];
-    for (int w = lane_id(); w < d.WW; w += 32) row[wid][w] = 0;
-    __syncwarp();
-    if (ctl[f].nruns[0] > 0) {
-        int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-        for (int id = r0 + lane_id(); id < r1; id += 32) {
-            int root = b.parent[id];
-            if (!(b.flag[root] & 1)) continue;
-            Run r = b.runs[id];
-            for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
-                int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
-                atomicOr(&row[wid][w], bit_range(blo, bhi));
-            }
-            if (root != id) continue;
-            // this run is the raster-first run of an edge component: allocate its contour
-            int ci = atomicAdd(&ctl[f].ncomp[0], 1);
-            int hh = b.ymax[id] - y + 1;
-            int slot = atomicAdd(&ctl[f].nslots[0], hh);
-            int ho = atomicAdd(&ctl[f].nhull[0], 2 * hh + 2);
-            if (ci >= cb.maxcomp || slot + hh > cb.slotcap || ho + 2 * hh + 2 > cb.hullcap) {
-                atomicOr(&ctl[f].status, LFD_FRAME_OVERFLOW);
-                continue;
-            }
-            cb.root[ci] = id;
-            cb.y0[ci] = y;
-            cb.h[ci] = hh;
-            cb.slot[ci] = slot;
-            cb.hulloff[ci] = ho;
-            for (int i = 0; i < hh; i++) { cb.rowmin[slot + i] = 0x7fffffff; cb.rowmax[slot + i] = -1; }
-            b.compidx[id] = ci;
-        }
-    }
-    __syncwarp();
-    for (int w = lane_id(); w < d.WW; w += 32) edges[(size_t)f * d.NW + (size_t)y * d.WW + w] = row[wid][w];
-}
-
-// 8. per-row extremes of every contour's point set
-__global__ void __launch_bounds__(CCL_WARPS * 32)
-k_ccl_extremes(const u32* __restrict__ edges, CclBuf* __restrict__ bufs, CompBuf* __restrict__ comps,
-               const FrameCtl* __restrict__ ctl, int pass, Dims d, int kind)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    int y = blockIdx.x * CCL_WARPS + (threadIdx.x >> 5);
-    if (y >= d.H) return;
-    CclBuf b = bufs[f];
-    CompBuf cb = comps[f];
-    if (ctl[f].nruns[kind] == 0) return;
-    const u32* em = edges + (size_t)f * d.NW;
-    int r0 = b.rowbase[y], r1 = b.rowbase[y + 1];
-    for (int id = r0 + lane_id(); id < r1; id += 32) {
-        int e = b.compidx[b.parent[id]];
-        if (e < 0) continue;
-        Run r = b.runs[id];
-        int s = cb.slot[e] + (y - cb.y0[e]);
-        if (kind == 0) {
-            atomicMin(&cb.rowmin[s], (int)r.xs);
-            atomicMax(&cb.rowmax[s], (int)r.xe);
-        } else {
-            // hole run [xs, xe] on row y (never on the frame border): edge pixels 4-adjacent to it
-            atomicMin(&cb.rowmin[s], (int)r.xs - 1);
-            atomicMax(&cb.rowmax[s], (int)r.xe + 1);
-            for (int dy = -1; dy <= 1; dy += 2) {
-                int yy = y + dy;
-                int first = -1, last = -1;
-                for (int w = r.xs >> 5; w <= (r.xe >> 5); w++) {
-                    int blo = max((int)r.xs - (w << 5), 0), bhi = min((int)r.xe - (w << 5), 31);
-                    u32 bits = em[(size_t)yy * d.WW + w] & bit_range(blo, bhi);
-                    if (bits) {
-                        if (first < 0) first = (w << 5) + __ffs(bits) - 1;
-                        last = (w << 5) + 31 - __clz(bits);
-                    }
-                }
-                if (first >= 0) {
-                    atomicMin(&cb.rowmin[s + dy], first);
-                    atomicMax(&cb.rowmax[s + dy], last);
-                }
-            }
-        }
-    }
-}
-
-// ---- flat (one thread per run) variants of steps 5-8 ---------------------------------------------------
+// ---- steps 5-8: one thread per run ---------------------------------------------------------------------
 // A frame has ~10-40 runs per row, so a warp-per-row grid leaves most lanes idle and launches ~1500 warps per
 // frame that each wait on the same chain of dependent loads.  Runs are stored contiguously per frame
 // (id = raster order), so these kernels simply stride over [0, nruns): full warps, 3x fewer of them.

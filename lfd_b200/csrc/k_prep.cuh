@@ -161,24 +161,6 @@ __device__ __forceinline__ u32 csa_fast(float v)
     return r;
 }
 
-// histogram update for four packed u8 values: bins 0..2 (nearly all pixels of a sky-subtracted frame)
-// are counted 4 at a time with SIMD byte compares + popc into registers; anything larger goes to
-// shared-memory atomics.
-__device__ __forceinline__ void hist4(u32 g, u32& n0, u32& n1, u32& n2, u32* sh)
-{
-    n0 += __popc(__vcmpeq4(g, 0x00000000u));
-    n1 += __popc(__vcmpeq4(g, 0x01010101u));
-    n2 += __popc(__vcmpeq4(g, 0x02020202u));
-    u32 big = __vcmpgtu4(g, 0x02020202u);
-    if (big) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            u32 c = (g >> (8 * k)) & 0xffu;
-            if (c > 2) atomicAdd(&sh[c], 1u);
-        }
-    }
-}
-
 // rint to u8 for 0 <= a < 256: a + 2^23 leaves round-half-even(a) in the low mantissa byte (FADD rounds to
 // nearest even) - one full-rate FP32 instruction instead of a quarter-rate F2I.  Anything that needs
 // saturation or special handling (a >= 255.5, |v| >= 2^31, inf - which cv2 maps to 0, not 255) shows up as a

@@ -16,49 +16,6 @@ struct RectBuf {
     float* hullf;        // [3*hullcap]
 };
 
-// one thread per contour
-__global__ void __launch_bounds__(128)
-k_rects(CompBuf* __restrict__ comps, RectBuf* __restrict__ rbufs, const CclBuf* __restrict__ ccl0,
-        const CclBuf* __restrict__ ccl1, FrameCtl* __restrict__ ctl, int pass,
-        Dims d, double minLen, double lwTresh)
-{
-    int f = blockIdx.y;
-    if (!ctl[f].active[pass]) return;
-    CompBuf cb = comps[f];
-    RectBuf rb = rbufs[f];
-    int n0 = min(ctl[f].ncomp[0], cb.maxcomp), n1 = min(ctl[f].ncomp[1], cb.maxcomp);
-    int total = n0 + n1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int kind = i >= n0;
-        int e = kind ? cb.maxcomp + (i - n0) : i;
-        int hh = cb.h[e], slot = cb.slot[e], ho = cb.hulloff[e], y0 = cb.y0[e];
-        lfdgeom::Pt* st = rb.hull + ho;
-        float* vect = rb.hullf + 3 * (size_t)ho;
-        int start;
-        int n = lfdgeom::hull_from_rows(cb.rowmin + slot, cb.rowmax + slot, hh, y0, st, &start);
-        lfdgeom::Rect r;
-        lfdgeom::min_area_rect(st, n, start, vect, vect + 2 * (size_t)(2 * hh + 2), &r);
-        lfd_rect o;
-        o.cx = r.cx; o.cy = r.cy; o.w = r.w; o.h = r.h; o.angle = r.angle;
-        o.kind = kind;
-        Run rr = (kind ? ccl1[f] : ccl0[f]).runs[cb.root[e]];   // raster-first run of the component / hole
-        o.key = (int)rr.y * d.W + (int)rr.xs;
-        float length = r.w > r.h ? r.w : r.h, width = r.w > r.h ? r.h : r.w;
-        int passed = 0;
-        if ((double)length > minLen && (double)width > minLen)
-            if ((double)length / (double)width > lwTresh) passed = 1;
-        o.passed = passed;
-        float f8[8];
-        lfdgeom::box_points(r, f8, o.box);
-        rb.rects[e] = o;
-        if (passed) {
-            ctl[f].hough[pass] = 1;
-            int pi = atomicAdd(&ctl[f].npass, 1);
-            rb.passing[pi] = e;
-        }
-    }
-}
-
 // ---- production kernel -------------------------------------------------------------------------------
 // Contours of ALL frames of the batch form one flat task list (prefix sums of the per-frame counts in
 // shared memory), 32 consecutive tasks per warp:

@@ -1157,8 +1157,9 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     k_ccl_rowscan<<<n, 1024, 0, s>>>(h->ccl_d[pass][0], C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_stats<<<rows, CCL_WARPS * 32, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
-    k_ccl_edges<<<rows, CCL_WARPS * 32, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], C, pass, d); LAUNCH_CHECK();
+    CK(cudaMemsetAsync(h->edges[pass], 0, (size_t)d.NW * sizeof(u32), s));
+    k_ccl_stats_flat<<<dim3(CCL_FLAT_CTAS, n), 256, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
+    k_ccl_alloc_flat<<<dim3(CCL_FLAT_CTAS, n), 256, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
     k_expand_mask<<<dim3(592, 1), 256, 0, s>>>(h->edges[pass], h->tap_u8, d); LAUNCH_CHECK();
     FrameCtl out;
     CK(cudaMemcpyAsync(&out, C, sizeof(out), cudaMemcpyDeviceToHost, s));
