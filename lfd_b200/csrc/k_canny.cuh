@@ -129,27 +129,28 @@ k_canny_nms(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
 #include "k_morph.cuh"
 
 #define NMS_R 32
+#define NMS_WPC 1                // warps (= strip units) per CTA: units differ a lot in work (skips), so small CTAs free their slot sooner
 
 __device__ __forceinline__ u32 vneg2(u32 a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ u32 vsub2(u32 a, u32 b) { return __vadd2(a, vneg2(b)); }
 __device__ __forceinline__ u32 vabs2s(u32 a) { return __vmaxs2(a, vneg2(a)); }
 
 template <bool TAP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NMS_WPC * 32)
 k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restrict__ cand, u32* __restrict__ strong,
             u8* __restrict__ nms_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int nstrips, int nunits,
             int low, int high)
 {
     const int f = blockIdx.y;
     if (!ctl[f].active[pass]) return;
-    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int unit = blockIdx.x * NMS_WPC + (threadIdx.x >> 5);
     if (unit >= nunits) return;
     // per warp: 3-row rings of magnitude / dx / dy as 16-bit planes of the 256-px strip.  The SIMD stage
     // writes them in "8 px per lane" layout, the decision stage reads them in "1 px per lane" layout, so
     // a 10-px run of gradient pixels occupies 10 lanes for one iteration instead of 2 lanes for 8.
-    __shared__ __align__(16) u16 sM[4][3][256];
-    __shared__ __align__(16) short sDX[4][3][256];
-    __shared__ __align__(16) short sDY[4][3][256];
+    __shared__ __align__(16) u16 sM[NMS_WPC][3][256];
+    __shared__ __align__(16) short sDX[NMS_WPC][3][256];
+    __shared__ __align__(16) short sDY[NMS_WPC][3][256];
     const int wid = threadIdx.x >> 5;
     const int chunk = unit / nstrips, s = unit - chunk * nstrips;
     const int lane = lane_id();

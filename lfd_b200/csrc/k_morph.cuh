@@ -167,6 +167,7 @@ k_morph(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict_
 #define MARCH_R 64            // output rows per warp
 #define MARCH_UW 56           // useful words per strip (7 mask words)
 #define MARCH_HW 4            // halo words per side (lanes 0,1 and 30,31)
+#define MARCH_WPC 1           // warps (= strip units) per CTA
 
 template <bool IS_MAX> __device__ __forceinline__ u32 mm2(u32 a, u32 b) { return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b); }
 template <bool IS_MAX> __device__ __forceinline__ u32 mm3(u32 a, u32 b, u32 c)
@@ -247,7 +248,7 @@ __device__ __forceinline__ u32 nzbits4(u32 w)
 }
 
 template <int EH, int EW, int DH, int DW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MARCH_WPC * 32)
 k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict__ morph, u32* __restrict__ nz,
               u8* __restrict__ eroded_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int nstrips, int nunits)
 {
@@ -256,7 +257,7 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
     __shared__ u8 slut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) slut[i] = lut[(size_t)f * 256 + i];
     __syncthreads();
-    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int unit = blockIdx.x * MARCH_WPC + (threadIdx.x >> 5);
     if (unit >= nunits) return;
     const int chunk = unit / nstrips, s = unit - chunk * nstrips;
     constexpr bool HAS_E = EH > 0;

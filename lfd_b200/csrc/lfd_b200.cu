@@ -649,7 +649,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         const u8* lutp = h->lut + ((size_t)pass * h->B + f0) * 256;
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + MARCH_R - 1) / MARCH_R;
         const int nunits = nstrips * nchunks;
-        dim3 gg((nunits + 3) / 4, n);
+        dim3 gg((nunits + MARCH_WPC - 1) / MARCH_WPC, n);
         bool done = false;
         if (h->anyk_on[pass]) {
             const AnyKernel* ekd = (pass == 1 && h->anyk_h[pass][0].n > 0) ? h->anyk_d + pass * 2 : nullptr;
@@ -661,7 +661,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         }
 #define MORPH_CASE(EH_, EW_, DH_, DW_)                                                                              \
         if (!done && (d.W % 8) == 0 && mc.eh == EH_ && mc.ew == EW_ && mc.dh == DH_ && mc.dw == DW_) {                \
-            k_morph_march<EH_, EW_, DH_, DW_><<<gg, 128, 0, s>>>(v_gray, lutp, v_morph, v_nz, etap, \
+            k_morph_march<EH_, EW_, DH_, DW_><<<gg, MARCH_WPC * 32, 0, s>>>(v_gray, lutp, v_morph, v_nz, etap, \
                                                                C, pass, d, nstrips, nunits);                    \
             done = true;                                                                                             \
         }
@@ -688,9 +688,9 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
-        dim3 gg((nunits + 3) / 4, n);
-        if (ntap) k_nms_march<true><<<gg, 128, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
-        else k_nms_march<false><<<gg, 128, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
+        dim3 gg((nunits + NMS_WPC - 1) / NMS_WPC, n);
+        if (ntap) k_nms_march<true><<<gg, NMS_WPC * 32, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
+        else k_nms_march<false><<<gg, NMS_WPC * 32, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, nstrips, nunits, 0, 255);
     } else {
         dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
         k_canny_nms<<<cg, 256, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, 0, 255);
@@ -1143,7 +1143,7 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
-        k_nms_march<false><<<dim3((nunits + 3) / 4, n), 128, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d,
+        k_nms_march<false><<<dim3((nunits + NMS_WPC - 1) / NMS_WPC, n), NMS_WPC * 32, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d,
                                                                   nstrips, nunits, low, high);
     } else {
         dim3 cg((d.W + CANNY_TW - 1) / CANNY_TW, (d.H + CANNY_TH - 1) / CANNY_TH, n);
