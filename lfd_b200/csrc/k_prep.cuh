@@ -173,22 +173,6 @@ __device__ __forceinline__ u32 pack_low_bytes(u32 u0, u32 u1, u32 u2, u32 u3)
     return __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
 }
 
-// histogram of four packed u8 values.  Sky-subtracted frames are almost entirely 0 (not counted at all: the zero
-// bin is the remainder) and 1 (one popc); anything else goes to shared-memory atomics.
-__device__ __forceinline__ void hist4_fast(u32 g, u32& n1, u32& nbig, u32* sh)
-{
-    n1 += __popc(g);                               // exact when every byte is 0 or 1 ...
-    if (g & 0xfefefefeu) {                         // ... otherwise (rare) take it back and count byte by byte
-        n1 -= __popc(g);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            u32 c = (g >> (8 * k)) & 0xffu;
-            if (c == 1u) n1++;
-            else if (c >= 2u) { atomicAdd(&sh[c], 1u); nbig++; }
-        }
-    }
-}
-
 // one float4: mask, clips, both conversions.  t[] are the un-flipped-source pixels of 4 consecutive columns.
 template <int MODE>
 __device__ __forceinline__ void prep4(float4 v, u32 mb, int bigendian, float minFlux, float addFlux, u32& g0, u32& g1)
@@ -234,77 +218,252 @@ __device__ __forceinline__ void prep4(float4 v, u32 mb, int bigendian, float min
     }
 }
 
-// MODE 0: pipeline (mask + flip, both passes) ; 1: bright only ; 2: dim only (no bright clip).
-// One CTA walks whole rows (no integer division); a thread converts 2 x 4 px per iteration, both 16-byte
-// loads issued before either is processed (bytes in flight per SM are what bounds a streaming kernel).
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0, u8* __restrict__ gray1,
-       u32* __restrict__ hist0, u32* __restrict__ hist1, Dims d, int bigendian, float minFlux, float addFlux)
+// ================================================================================================
+// k_prep: the batch-pipeline kernel.  The float frames are staged through shared memory by the TMA engine.
+// Every warp owns a ring of PR_S stages of PR_CB bytes (one stage = 512 consecutive pixels of a row) filled by
+// 1-D bulk-async copies (cp.async.bulk -> UBLKCP) that complete on the warp's own mbarriers: lane 0 re-arms a
+// stage as soon as the warp has consumed it, so the bytes in flight per SM (PR_WARPS x PR_S x 2 KB per CTA) no
+// longer depend on registers or on how many warps are stalled, and no __syncthreads is needed in the loop.
+// Per chunk a lane converts four float4 (q = lane + 32k: conflict-free LDS.128, 128-byte coalesced stores),
+// the star-mask words of the chunk are fetched one chunk ahead (16 words, one per lane) and skipped with a
+// single vote when the chunk holds no blotted pixel, and the histogram bookkeeping is per chunk: bin 1 by
+// dp4a byte sums, one test for "any byte >= 2" over the eight output words.
+// ================================================================================================
+#define PR_WARPS 8
+#define PR_S 2
+#define PR_Q 4                              // float4 per lane per chunk
+#define PR_CF4 (32 * PR_Q)                  // float4 per chunk
+#define PR_CB (PR_CF4 * 16)                 // bytes per chunk
+#define PR_SMEM (PR_WARPS * PR_S * PR_CB + 2 * 256 * 4 + PR_WARPS * PR_S * 8 + PR_WARPS * 2 * 256 * 4)
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar)
 {
-    // grid = (rows-CTAs per frame, frames), sized by the host to one wave of resident CTAs.  A CTA walks whole
-    // rows (no integer division), two rows per iteration: a thread issues four 16-byte loads before it converts
-    // anything - bytes in flight per SM, not instruction issue, bound this streaming kernel.
-    __shared__ u32 sh[2][256];
-    const int f = blockIdx.y;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0;
-    __syncthreads();
-    const float* src = in + (size_t)f * d.N;
-    const int wq = d.W >> 2;
-    u32 a1 = 0, abig = 0, b1 = 0, bbig = 0, nwords = 0;
-    for (int ya = blockIdx.x; ya < d.H; ya += 2 * gridDim.x) {
-        const int yb = ya + gridDim.x;
-        const bool rowb = yb < d.H;
-        const int ybc = rowb ? yb : ya;
-        const int sya = (MODE == 0) ? (d.H - 1 - ya) : ya, syb = (MODE == 0) ? (d.H - 1 - ybc) : ybc;
-        const float4* srowa = reinterpret_cast<const float4*>(src + (size_t)sya * d.W);
-        const float4* srowb = reinterpret_cast<const float4*>(src + (size_t)syb * d.W);
-        const u32* mrowa = mask + (size_t)f * d.NW + (size_t)ya * d.WW;
-        const u32* mrowb = mask + (size_t)f * d.NW + (size_t)ybc * d.WW;
-        u32* o0a = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)ya * d.W);
-        u32* o1a = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)ya * d.W);
-        u32* o0b = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N + (size_t)ybc * d.W);
-        u32* o1b = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N + (size_t)ybc * d.W);
-        for (int xq = threadIdx.x; xq < wq; xq += 2 * blockDim.x) {
-            const int xq2 = xq + blockDim.x;
-            const bool two = xq2 < wq;
-            const int xq2c = two ? xq2 : xq;
-            float4 v[4];
-            v[0] = __ldcs(srowa + xq); v[1] = __ldcs(srowa + xq2c);
-            v[2] = __ldcs(srowb + xq); v[3] = __ldcs(srowb + xq2c);
-            u32 m[4] = {0, 0, 0, 0};
-            if (MODE == 0) {
-                m[0] = (__ldg(mrowa + (xq >> 3)) >> ((xq & 7) << 2)) & 0xfu;
-                m[1] = (__ldg(mrowa + (xq2c >> 3)) >> ((xq2c & 7) << 2)) & 0xfu;
-                m[2] = (__ldg(mrowb + (xq >> 3)) >> ((xq & 7) << 2)) & 0xfu;
-                m[3] = (__ldg(mrowb + (xq2c >> 3)) >> ((xq2c & 7) << 2)) & 0xfu;
-            }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
+{
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Pipeline-mode conversion of one float4 (mask + bright clip -> g0 ; + dim threshold/offset -> g1).
+// After the bright clip t is never negative or NaN, so the two dim conditions "not (t < minFlux)" and "t > 0"
+// (processfield.py:453-454) are the single compare t >= thr, thr = minFlux > 0 ? minFlux : smallest denormal.
+template <bool BE>
+__device__ __forceinline__ void prep4_pipe(float4 v, u32 mb, float thr, float minFlux, float addFlux, u32& g0, u32& g1)
+{
+    if (BE) { v.x = bswapf(v.x); v.y = bswapf(v.y); v.z = bswapf(v.z); v.w = bswapf(v.w); }
+    if (mb) {
+        if (mb & 1u) v.x = 0.0f;
+        if (mb & 2u) v.y = 0.0f;
+        if (mb & 4u) v.z = 0.0f;
+        if (mb & 8u) v.w = 0.0f;
+    }
+    const float t[4] = {v.x, v.y, v.z, v.w};
+    u32 a[4], b[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool on = (k == 0) || (k == 1 && two) || (k == 2 && rowb) || (k == 3 && two && rowb);
-                if (!on) continue;
-                u32 g0, g1;
-                prep4<MODE>(v[k], m[k], bigendian, minFlux, addFlux, g0, g1);
-                const int xo = (k & 1) ? xq2 : xq;
-                if (MODE != 2) { ((k & 2) ? o0b : o0a)[xo] = g0; hist4_fast(g0, a1, abig, sh[0]); }
-                if (MODE != 1) { ((k & 2) ? o1b : o1a)[xo] = g1; hist4_fast(g1, b1, bbig, sh[1]); }
-                nwords++;
-            }
+    for (int k = 0; k < 4; k++) {
+        const float tt = fmaxf(t[k], 0.0f);              // v < 0 -> 0 ; NaN -> 0 (the reference keeps NaN, which converts to 0 too)
+        a[k] = rint_bits(tt);
+        const float s = __fadd_rn(tt, addFlux);
+        b[k] = rint_bits((tt >= thr) ? s : 0.0f);
+    }
+    g0 = pack_low_bytes(a[0], a[1], a[2], a[3]);
+    g1 = pack_low_bytes(b[0], b[1], b[2], b[3]);
+    if ((a[0] | a[1] | a[2] | a[3] | b[0] | b[1] | b[2] | b[3]) & RINT_BITS_OVERFLOW) {    // rare: exact redo
+        g0 = 0; g1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float tt = fmaxf(t[k], 0.0f);
+            g0 |= csa_fast(tt) << (8 * k);
+            float bb = (tt < minFlux) ? 0.0f : tt;
+            bb = (bb > 0.0f) ? __fadd_rn(bb, addFlux) : bb;
+            g1 |= csa_fast(bb) << (8 * k);
         }
     }
-    // bins 1 and 0 from the register counters (0 = everything that was not counted elsewhere)
+}
+
+// Exact bookkeeping of one word that may hold bytes >= 2 (n1 already holds the word's dp4a byte sum): a SWAR test
+// marks the bytes >= 2, those go to shared-memory atomics one by one (predicated, no nested branches), bin 1 is
+// corrected to the number of bytes that are exactly 1.
+__device__ __forceinline__ void hist4_fix(u32 g, u32& n1, u32& nbig, u32* sh)
+{
+    const u32 m2 = g & 0xfefefefeu;
+    const u32 t = (((m2 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m2) & 0x80808080u;     // bit 7 of every byte that is >= 2
+    if (t) {
+        n1 += __popc(g & 0x01010101u & ~(t >> 7)) - __dp4a(g, 0x01010101u, 0u);
+        nbig += __popc(t);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (t & (0x80u << (8 * k))) atomicAdd(&sh[(g >> (8 * k)) & 0xffu], 1u);
+    }
+}
+
+// Words with a byte >= 2 (star pixels) are not histogrammed where they are produced: a shared-memory atomic issued
+// from the conversion loop with one or two active lanes costs the warp ~150 cycles each (measured: a dense field
+// took 25 % longer than a sparse one for 1.4 % such words).  They are appended to a per-warp staging list instead
+// (ballot + popc slot allocation, plain stores) and histogrammed 32 words at a time with all lanes active.
+#define PR_STG 256                          // staging words per warp and plane; one chunk adds at most 128
+__device__ __forceinline__ void stage_big(const u32 (&G)[PR_Q], u32* stg, int& base, int lane)
+{
+    const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < PR_Q; k++) {
+        const bool big = (G[k] & 0xfefefefeu) != 0u;
+        const u32 b = __ballot_sync(FULLMASK, big);
+        if (big) stg[base + __popc(b & lt)] = G[k];
+        base += __popc(b);
+    }
+}
+__device__ __forceinline__ void drain_big(const u32* stg, int& base, u32& n1, u32& nbig, u32* sh, int lane)
+{
+    __syncwarp();
+    for (int i = lane; i < base; i += 32) hist4_fix(stg[i], n1, nbig, sh);
+    __syncwarp();
+    base = 0;
+}
+
+// MODE 0: pipeline (mask + flip, both passes) ; 1: bright only ; 2: dim only (no bright clip).
+// grid = (CTAs per frame, frames), one resident wave; dynamic shared memory PR_SMEM bytes.
+template <int MODE, bool BE, int MINB = 4>
+__global__ void __launch_bounds__(PR_WARPS * 32, MINB)
+k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0, u8* __restrict__ gray1,
+            u32* __restrict__ hist0, u32* __restrict__ hist1, Dims d, int nframes, float minFlux, float addFlux)
+{
+    extern __shared__ __align__(128) unsigned char dsm[];
+    float4* ring = reinterpret_cast<float4*>(dsm);                                       // [PR_WARPS][PR_S][PR_CF4]
+    u32* sh = reinterpret_cast<u32*>(dsm + (size_t)PR_WARPS * PR_S * PR_CB);             // [2][256]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 512);          // [PR_WARPS][PR_S]
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32* stg0 = reinterpret_cast<u32*>(bars + PR_WARPS * PR_S) + (size_t)wid * 2 * PR_STG;   // [PR_WARPS][2][PR_STG]
+    u32* stg1 = stg0 + PR_STG;
+    int nst0 = 0, nst1 = 0;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0;
+    if (lane == 0)
+        for (int s = 0; s < PR_S; s++) mbar_init(smem_u32(&bars[wid * PR_S + s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int rowb = d.W * 4;                          // bytes per row (a multiple of 16: W % 4 == 0)
+    const int cpr = (rowb + PR_CB - 1) / PR_CB;        // chunks per row
+    const int total = d.H * cpr;
+    const int stride = gridDim.x * PR_WARPS;
+    const int dy = stride / cpr, dj = stride - dy * cpr;
+    const float thr = (minFlux > 0.0f) ? minFlux : __int_as_float(1);
+    const u32 ring0 = smem_u32(ring + (size_t)wid * PR_S * PR_CF4);
+    const u32 bar0 = smem_u32(&bars[wid * PR_S]);
+
+    // gridDim.y frames are in flight at a time (each frame read and written as three sequential streams: fewer
+    // concurrent streams keep more DRAM pages open); a CTA walks the frames blockIdx.y, blockIdx.y + gridDim.y, ...
+    int ps = 0, cs = 0; u32 cpar = 0;                  // ring stage of the producer / consumer, consumer phase parity
+    for (int f = blockIdx.y; f < nframes; f += gridDim.y) {
+    const char* src = reinterpret_cast<const char*>(in + (size_t)f * d.N);
+    const u32* mf = mask + (size_t)f * d.NW;
+    u32* o0 = reinterpret_cast<u32*>(gray0 + (size_t)f * d.N);
+    u32* o1 = reinterpret_cast<u32*>(gray1 + (size_t)f * d.N);
+    // producer state (next chunk to request) and consumer state (next chunk to convert)
+    int pc = blockIdx.x * PR_WARPS + wid, py = pc / cpr, pj = pc - py * cpr;
+    int cc = pc, cy = py, cj = pj;
+    auto issue = [&]() {
+        if (pc < total) {
+            if (lane == 0) {
+                const int sy = (MODE == 0) ? (d.H - 1 - py) : py;
+                const u32 nb = (u32)min(PR_CB, rowb - pj * PR_CB);
+                mbar_expect_tx(bar0 + 8 * ps, nb);
+                bulk_g2s(ring0 + ps * PR_CB, src + (size_t)sy * rowb + (size_t)pj * PR_CB, nb, bar0 + 8 * ps);
+            }
+            pc += stride; py += dy; pj += dj; if (pj >= cpr) { pj -= cpr; py++; }
+            ps = (ps + 1 == PR_S) ? 0 : ps + 1;
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < PR_S; s++) issue();
+
+    auto load_mask = [&](int y, int j) -> u32 {
+        if (MODE != 0) return 0u;
+        const int w = j * (4 * PR_Q) + lane;
+        return (lane < 4 * PR_Q && w < d.WW) ? __ldg(mf + y * d.WW + w) : 0u;
+    };
+    u32 mword = (cc < total) ? load_mask(cy, cj) : 0u;
+    u32 a1 = 0, abig = 0, b1 = 0, bbig = 0, nwords = 0;
+    while (cc < total) {
+        const int nf4 = min(PR_CF4, (rowb - cj * PR_CB) >> 4);
+        const int xo = ((cy * d.W + cj * (PR_CB / 4)) >> 2) + lane;     // u32 index of this lane's first output word
+        const u32 mcur = mword;
+        cc += stride; cy += dy; cj += dj; if (cj >= cpr) { cj -= cpr; cy++; }
+        if (cc < total) mword = load_mask(cy, cj);                      // next chunk's mask words, one chunk ahead
+        mbar_wait(bar0 + 8 * cs, cpar);
+        const float4* buf = ring + ((size_t)wid * PR_S + cs) * PR_CF4 + lane;
+        float4 v[PR_Q];
+#pragma unroll
+        for (int k = 0; k < PR_Q; k++) v[k] = buf[32 * k];
+        const bool anym = (MODE == 0) ? __any_sync(FULLMASK, mcur != 0u) : false;
+        u32* p0 = o0 + xo; u32* p1 = o1 + xo;
+        u32 G0[PR_Q], G1[PR_Q];
+#pragma unroll
+        for (int k = 0; k < PR_Q; k++) {
+            u32 mb = 0;
+            if (anym) mb = (__shfl_sync(FULLMASK, mcur, (lane >> 3) + 4 * k) >> ((lane & 7) << 2)) & 0xfu;
+            if (MODE == 0) prep4_pipe<BE>(v[k], mb, thr, minFlux, addFlux, G0[k], G1[k]);
+            else prep4<MODE>(v[k], 0u, BE ? 1 : 0, minFlux, addFlux, G0[k], G1[k]);
+        }
+        if (nf4 == PR_CF4) {
+#pragma unroll
+            for (int k = 0; k < PR_Q; k++) {
+                if (MODE != 2) p0[32 * k] = G0[k];
+                if (MODE != 1) p1[32 * k] = G1[k];
+            }
+            nwords += PR_Q;
+        } else {                                                        // last chunk of a row when 4W % PR_CB != 0
+#pragma unroll
+            for (int k = 0; k < PR_Q; k++) {
+                if (lane + 32 * k < nf4) {
+                    if (MODE != 2) p0[32 * k] = G0[k];
+                    if (MODE != 1) p1[32 * k] = G1[k];
+                    nwords++;
+                } else { G0[k] = 0u; G1[k] = 0u; }
+            }
+        }
+        // histogram: bin 1 = byte sums (exact while every byte is 0 or 1), bin 0 = remainder, anything else is rare
+        u32 or0 = 0, or1 = 0;
+#pragma unroll
+        for (int k = 0; k < PR_Q; k++) {
+            if (MODE != 2) { a1 = __dp4a(G0[k], 0x01010101u, a1); or0 |= G0[k]; }
+            if (MODE != 1) { b1 = __dp4a(G1[k], 0x01010101u, b1); or1 |= G1[k]; }
+        }
+        if (MODE != 2 && __any_sync(FULLMASK, (or0 & 0xfefefefeu) != 0u)) {
+            if (nst0 > PR_STG - 32 * PR_Q) drain_big(stg0, nst0, a1, abig, sh, lane);
+            stage_big(G0, stg0, nst0, lane);
+        }
+        if (MODE != 1 && __any_sync(FULLMASK, (or1 & 0xfefefefeu) != 0u)) {
+            if (nst1 > PR_STG - 32 * PR_Q) drain_big(stg1, nst1, b1, bbig, sh + 256, lane);
+            stage_big(G1, stg1, nst1, lane);
+        }
+        __syncwarp();                                                   // every lane has consumed the stage
+        issue();                                                        // ... so it can be refilled
+        cs++; if (cs == PR_S) { cs = 0; cpar ^= 1u; }
+    }
+    if (MODE != 2) drain_big(stg0, nst0, a1, abig, sh, lane);
+    if (MODE != 1) drain_big(stg1, nst1, b1, bbig, sh + 256, lane);
     u32 acc[4] = {a1, 4u * nwords - a1 - abig, b1, 4u * nwords - b1 - bbig};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         u32 vsum = acc[k];
         for (int o = 16; o; o >>= 1) vsum += __shfl_xor_sync(FULLMASK, vsum, o);
-        if (lane_id() == 0 && vsum) atomicAdd(&sh[k >> 1][(k & 1) ? 0 : 1], vsum);
+        if (lane == 0 && vsum) atomicAdd(&sh[(k >> 1) * 256 + ((k & 1) ? 0 : 1)], vsum);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        if (MODE != 2 && sh[0][i]) atomicAdd(&hist0[(size_t)f * 256 + i], sh[0][i]);
-        if (MODE != 1 && sh[1][i]) atomicAdd(&hist1[(size_t)f * 256 + i], sh[1][i]);
+        if (MODE != 2 && sh[i]) atomicAdd(&hist0[(size_t)f * 256 + i], sh[i]);
+        if (MODE != 1 && sh[256 + i]) atomicAdd(&hist1[(size_t)f * 256 + i], sh[256 + i]);
+        sh[i] = 0; sh[256 + i] = 0;
     }
+    __syncthreads();
+    }   // frames
 }
 
 // cv2.equalizeHist's LUT from the 256-bin histogram; one 256-thread block per (frame, pass).

@@ -386,9 +386,13 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         int per_sm[3] = {0, 0, 0};
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_prep<0>, 256, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_prep<1>, 256, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_prep<2>, 256, 0));
+        // k_prep keeps its TMA rings in dynamic shared memory (above the 48 KB default limit)
+#define PREP_ATTR(M, E) CK(cudaFuncSetAttribute(k_prep<M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM))
+        PREP_ATTR(0, false); PREP_ATTR(0, true); PREP_ATTR(1, false); PREP_ATTR(1, true); PREP_ATTR(2, false); PREP_ATTR(2, true);
+#undef PREP_ATTR
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_prep<0, false>, PR_WARPS * 32, PR_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_prep<1, false>, PR_WARPS * 32, PR_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_prep<2, false>, PR_WARPS * 32, PR_SMEM));
         for (int m = 0; m < 3; m++) h->prep_grid[m] = prop.multiProcessorCount * (per_sm[m] > 0 ? per_sm[m] : 1);
     }
     // the dynamic shared-memory limit is a property of the FUNCTION, shared by every handle of the process: only ever raise it
@@ -778,11 +782,17 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     } else {
         // one wave of resident CTAs spread over the frames of the batch (a second, partial wave would double the time)
         const float mf = (float)pd.minFlux, af = (float)pd.addFlux;
-        int rb = h->prep_grid[mode] / n; if (rb < 1) rb = 1; if (rb > d.H) rb = d.H;
-        dim3 pg(rb, n);
-        if (mode == 0) k_prep<0><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
-        else if (mode == 1) k_prep<1><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
-        else k_prep<2><<<pg, 256, 0, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, be, mf, af);
+        // at most 32 frames in flight at a time (fewer concurrent DRAM streams); CTAs walk the rest of the batch
+        const int gy = n < 32 ? n : 32;
+        int rb = h->prep_grid[mode] / gy; if (rb < 1) rb = 1;
+        const int chunks = d.H * ((d.W * 4 + PR_CB - 1) / PR_CB);
+        if (rb > (chunks + PR_WARPS - 1) / PR_WARPS) rb = (chunks + PR_WARPS - 1) / PR_WARPS;
+        dim3 pg(rb, gy);
+#define PREP_LAUNCH(M, E) k_prep<M, E><<<pg, PR_WARPS * 32, PR_SMEM, s>>>(h->in, h->starmask, h->gray[0], h->gray[1], h->hist, hist1, d, n, mf, af)
+        if (mode == 0) { if (be) PREP_LAUNCH(0, true); else PREP_LAUNCH(0, false); }
+        else if (mode == 1) { if (be) PREP_LAUNCH(1, true); else PREP_LAUNCH(1, false); }
+        else { if (be) PREP_LAUNCH(2, true); else PREP_LAUNCH(2, false); }
+#undef PREP_LAUNCH
         LAUNCH_CHECK();
     }
     CK(cudaEventRecord(h->ev[2], s));
