@@ -454,8 +454,8 @@ def run_ours(args):
     for tr_path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")), reverse=True):
         try:
             t = json.load(open(tr_path))
-            if "k_prep_bytes_per_launch_b%d" % B in t:
-                roofline["traffic"] = t["k_prep_bytes_per_launch_b%d" % B]
+            if "k_prep_bytes_per_frame" in t and t.get("batch") == B:
+                roofline["traffic"] = t["k_prep_bytes_per_frame"] * B      # one k_prep launch covers the whole batch
                 roofline["traffic_source"] = "profiles/" + os.path.basename(tr_path)
                 break
         except Exception:

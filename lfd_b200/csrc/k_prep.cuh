@@ -162,11 +162,26 @@ __device__ __forceinline__ u32 csa_fast(float v)
 }
 
 // rint to u8 for 0 <= a < 256: a + 2^23 leaves round-half-even(a) in the low mantissa byte (FADD rounds to
-// nearest even) - one full-rate FP32 instruction instead of a quarter-rate F2I.  Anything that needs
-// saturation or special handling (a >= 255.5, |v| >= 2^31, inf - which cv2 maps to 0, not 255) shows up as a
-// non-zero bit in 0x00ffff00 of the sum's bit pattern and is redone exactly by the caller.
+// nearest even) - one full-rate FP32 instruction instead of a quarter-rate F2I.  The sum's bit pattern is
+// 0x4B0000xx exactly when 0 <= a < 255.5; anything that needs saturation or special handling (a >= 255.5,
+// |v| >= 2^31, inf - which cv2 maps to 0, not 255 -, NaN, and negative sums, whose sign bit makes them huge
+// unsigned numbers) is above RINT_BITS_MAX as an unsigned integer and is redone exactly by the caller; a sum
+// that rounds to just below 2^23 (a small negative a, only possible with a negative addFlux) is below
+// RINT_BITS_MIN.
 __device__ __forceinline__ u32 rint_bits(float a) { return __float_as_uint(__fadd_rn(a, 8388608.0f)); }
-#define RINT_BITS_OVERFLOW 0x00ffff00u
+#define RINT_BITS_MIN 0x4B000000u
+#define RINT_BITS_MAX 0x4B0000ffu
+// true when any of the eight sums needs the exact path (a[]: never negative; b[]: negative only if addFlux < 0)
+__device__ __forceinline__ bool rint_bits_special(const u32 (&a)[4], const u32 (&b)[4], bool b_may_be_negative)
+{
+    u32 m = __vimax3_u32(a[0], a[1], a[2]);
+    m = __vimax3_u32(m, a[3], b[0]);
+    m = __vimax3_u32(m, b[1], b[2]);
+    m = max(m, b[3]);
+    bool sp = m > RINT_BITS_MAX;
+    if (b_may_be_negative) sp = sp || min(min(b[0], b[1]), min(b[2], b[3])) < RINT_BITS_MIN;
+    return sp;
+}
 
 __device__ __forceinline__ u32 pack_low_bytes(u32 u0, u32 u1, u32 u2, u32 u3)
 {
@@ -185,7 +200,7 @@ __device__ __forceinline__ void prep4(float4 v, u32 mb, int bigendian, float min
         if (mb & 8u) v.w = 0.0f;
     }
     float t[4] = {v.x, v.y, v.z, v.w};
-    u32 a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    u32 a[4] = {RINT_BITS_MIN, RINT_BITS_MIN, RINT_BITS_MIN, RINT_BITS_MIN}, b[4] = {RINT_BITS_MIN, RINT_BITS_MIN, RINT_BITS_MIN, RINT_BITS_MIN};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float tt = t[k];
@@ -202,8 +217,8 @@ __device__ __forceinline__ void prep4(float4 v, u32 mb, int bigendian, float min
     }
     g0 = (MODE != 2) ? pack_low_bytes(a[0], a[1], a[2], a[3]) : 0u;
     g1 = (MODE != 1) ? pack_low_bytes(b[0], b[1], b[2], b[3]) : 0u;
-    // exact redo of the rare pixels that need saturation / special values
-    if ((a[0] | a[1] | a[2] | a[3] | b[0] | b[1] | b[2] | b[3]) & RINT_BITS_OVERFLOW) {
+    // exact redo of the rare pixels that need saturation / special values (MODE 2 converts |v|: never negative)
+    if (rint_bits_special(a, b, MODE == 0 && !(addFlux >= 0.0f))) {
         g0 = 0; g1 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -274,7 +289,7 @@ __device__ __forceinline__ void prep4_pipe(float4 v, u32 mb, float thr, float mi
     }
     g0 = pack_low_bytes(a[0], a[1], a[2], a[3]);
     g1 = pack_low_bytes(b[0], b[1], b[2], b[3]);
-    if ((a[0] | a[1] | a[2] | a[3] | b[0] | b[1] | b[2] | b[3]) & RINT_BITS_OVERFLOW) {    // rare: exact redo
+    if (rint_bits_special(a, b, !(addFlux >= 0.0f))) {                                     // rare: exact redo
         g0 = 0; g1 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -328,8 +343,9 @@ __device__ __forceinline__ void drain_big(const u32* stg, int& base, u32& n1, u3
 }
 
 // MODE 0: pipeline (mask + flip, both passes) ; 1: bright only ; 2: dim only (no bright clip).
-// grid = (CTAs per frame, frames), one resident wave; dynamic shared memory PR_SMEM bytes.
-template <int MODE, bool BE, int MINB = 4>
+// grid = (CTAs per frame, frames in flight), one resident wave; dynamic shared memory PR_SMEM bytes.
+// MINB = 3 resident CTAs per SM (72 registers): measured 3-5 % faster than 4 CTAs of 64 registers.
+template <int MODE, bool BE, int MINB = 3>
 __global__ void __launch_bounds__(PR_WARPS * 32, MINB)
 k_prep(const float* __restrict__ in, const u32* __restrict__ mask, u8* __restrict__ gray0, u8* __restrict__ gray1,
             u32* __restrict__ hist0, u32* __restrict__ hist1, Dims d, int nframes, float minFlux, float addFlux)

@@ -782,8 +782,9 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     } else {
         // one wave of resident CTAs spread over the frames of the batch (a second, partial wave would double the time)
         const float mf = (float)pd.minFlux, af = (float)pd.addFlux;
-        // at most 32 frames in flight at a time (fewer concurrent DRAM streams); CTAs walk the rest of the batch
-        const int gy = n < 32 ? n : 32;
+        // at most 16 frames in flight at a time (fewer concurrent DRAM streams: measured best of 16 / 24 / 32 / all
+        // with profiles/lab/prep_lab.cu); the CTAs of the single resident wave walk the rest of the batch
+        const int gy = n < 16 ? n : 16;
         int rb = h->prep_grid[mode] / gy; if (rb < 1) rb = 1;
         const int chunks = d.H * ((d.W * 4 + PR_CB - 1) / PR_CB);
         if (rb > (chunks + PR_WARPS - 1) / PR_WARPS) rb = (chunks + PR_WARPS - 1) / PR_WARPS;

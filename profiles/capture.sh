@@ -9,7 +9,7 @@ $CMD > $OUT/plain_$TAG.json 2> $OUT/plain_$TAG.err || { echo "plain run failed";
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_l_$TAG.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_prep|k_morph_march|k_nms_march|k_ccl_band|k_rects_warp|k_hough_vote|k_ccl_stats" -s 40 -c 16 \
+    -k regex:"k_prep|k_morph_march|k_nms_march|k_ccl_band|k_rects_warp|k_hough_vote|k_ccl_stats" -s 132 -c 33 \
     -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_f_$TAG.log 2>&1
 echo "full capture rc=$?"
 ncu -i $OUT/prof_$TAG.ncu-rep --page raw --csv > $OUT/prof_${TAG}_raw.csv 2>/dev/null

@@ -84,8 +84,9 @@ int main(int argc, char** argv)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 
     struct Var { std::string name; int id; bool check; };
-    std::vector<Var> vars = {{"k_prep_generic (reference)", 0, true}, {"k_prep G=min(B,32)", 132, true}, {"k_prep G=16", 116, true},
-                             {"k_prep G=B", 100 + B, true}, {"k_prep minb=3 G=32", 332, true}, {"k_prep minb=2 G=32", 232, true}, {"k_prep minb=3 G=16", 316, true}, {"k_prep minb=2 G=16", 216, true}, {"plain copy 16B->8B", 20, false}, {"memcpy d2d same bytes", 21, false}};
+    std::vector<Var> vars = {{"k_prep_generic (reference)", 0, true}, {"k_prep 3 CTAs/SM G=16 (library)", 316, true}, {"k_prep 3 CTAs/SM G=32", 332, true},
+                             {"k_prep 4 CTAs/SM G=16", 116, true}, {"k_prep 4 CTAs/SM G=24", 124, true}, {"k_prep 4 CTAs/SM G=32", 132, true},
+                             {"k_prep 4 CTAs/SM G=B", 100 + B, true}, {"plain copy 16B->8B", 20, false}, {"memcpy d2d same bytes", 21, false}};
     int per_sm = 0;
     CKL(cudaFuncSetAttribute(k_prep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
     CKL(cudaFuncSetAttribute(k_prep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
@@ -98,13 +99,14 @@ int main(int argc, char** argv)
             k_prep_generic<<<dim3(pblocks, B), 256>>>(in, mask, g0[slot], g1[slot], h0, h1, nullptr, d, 0, be, minFlux, addFlux);
         } else if (id >= 100 && id <= 199) {
             const int G = id - 100 > B ? B : id - 100;
-            int rb = nsm * per_sm / G; if (rb < 1) rb = 1;
-            if (be) k_prep<0, true><<<dim3(rb, G), PR_WARPS * 32, PR_SMEM>>>(in, mask, g0[slot], g1[slot], h0, h1, d, B, minFlux, addFlux);
-            else k_prep<0, false><<<dim3(rb, G), PR_WARPS * 32, PR_SMEM>>>(in, mask, g0[slot], g1[slot], h0, h1, d, B, minFlux, addFlux);
+            int rb = nsm * 4 / G; if (rb < 1) rb = 1;
+            auto kk = be ? k_prep<0, true, 4> : k_prep<0, false, 4>;
+            cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
+            kk<<<dim3(rb, G), PR_WARPS * 32, PR_SMEM>>>(in, mask, g0[slot], g1[slot], h0, h1, d, B, minFlux, addFlux);
         }
         else if (id >= 200 && id <= 399) {
             const int mb = id / 100, G = id % 100 > B ? B : id % 100;
-            auto kk = mb == 3 ? k_prep<0, false, 3> : k_prep<0, false, 2>;
+            auto kk = mb == 3 ? (be ? k_prep<0, true, 3> : k_prep<0, false, 3>) : k_prep<0, false, 2>;   // (100 + G selects the library default)
             cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM);
             int rb = nsm * mb / G; if (rb < 1) rb = 1;
             kk<<<dim3(rb, G), PR_WARPS * 32, PR_SMEM>>>(in, mask, g0[slot], g1[slot], h0, h1, d, B, minFlux, addFlux);
@@ -130,7 +132,7 @@ int main(int argc, char** argv)
         CKL(cudaMemset(g0[1], 0xee, (size_t)B * d.N)); CKL(cudaMemset(g1[1], 0xee, (size_t)B * d.N));
         launch(v.id, 1, 0);
         cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("%-22s FAILED: %s\n", v.name.c_str(), cudaGetErrorString(e)); return 1; }
+        if (e != cudaSuccess) { printf("%-32s FAILED: %s\n", v.name.c_str(), cudaGetErrorString(e)); return 1; }
         std::string verdict = "n/a";
         if (v.check) {
             CKL(cudaMemcpy(t0.data(), g0[1], t0.size(), cudaMemcpyDeviceToHost));
@@ -148,13 +150,13 @@ int main(int argc, char** argv)
         cudaEventRecord(e1);
         CKL(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
-        printf("%-22s %8.1f us  %7.1f GB/s  frac %.3f  %s\n", v.name.c_str(), 1e3 * ms / R, bytes / (ms / R * 1e-3) * 1e-9,
+        printf("%-32s %8.1f us  %7.1f GB/s  frac %.3f  %s\n", v.name.c_str(), 1e3 * ms / R, bytes / (ms / R * 1e-3) * 1e-9,
                bytes / (ms / R * 1e-3) * 1e-9 / 6553.9, verdict.c_str());
     }
     // big-endian input path: byte-swap the frames on the host side of the comparison = run both with be=1
     {
         CKL(cudaMemset(hist[0], 0, (size_t)2 * B * 256 * 4)); CKL(cudaMemset(hist[1], 0, (size_t)2 * B * 256 * 4));
-        launch(0, 0, 1); launch(132, 1, 1);
+        launch(0, 0, 1); launch(316, 1, 1);
         CKL(cudaDeviceSynchronize());
         CKL(cudaMemcpy(r0.data(), g0[0], r0.size(), cudaMemcpyDeviceToHost)); CKL(cudaMemcpy(t0.data(), g0[1], t0.size(), cudaMemcpyDeviceToHost));
         CKL(cudaMemcpy(r1.data(), g1[0], r1.size(), cudaMemcpyDeviceToHost)); CKL(cudaMemcpy(t1.data(), g1[1], t1.size(), cudaMemcpyDeviceToHost));

@@ -66,9 +66,12 @@ ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 for r in data:
     name = re.sub(r"<.*", "", r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")).strip()
     tr.setdefault(name, []).append(float(r[ir]) * mul[units[ir]] + float(r[iw]) * mul[units[iw]])
-traffic = {"batch": batch, "source": os.path.basename(raw), "unit": "bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch"}
+# batches of >= 16 frames run as two halves after k_prep, so every other launch of the profiled command covers
+# half the batch
+half = (batch + 1) // 2 if batch >= 16 else batch
+traffic = {"batch": batch, "frames_per_launch": {"k_prep": batch, "others": half}, "source": os.path.basename(raw), "unit": "bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch"}
 for k, v in tr.items():
     traffic["%s_bytes_per_launch_b%d" % (k, batch)] = sum(v) / len(v)
-    traffic["%s_bytes_per_frame" % k] = sum(v) / len(v) / batch
+    traffic["%s_bytes_per_frame" % k] = sum(v) / len(v) / (batch if k == "k_prep" else half)
 json.dump(traffic, open(os.path.join(P, "traffic_%s.json" % tag), "w"), indent=1)
 print("wrote traffic_%s.json" % tag)

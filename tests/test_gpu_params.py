@@ -131,6 +131,10 @@ def test_special_float_values(cv2mod):
     specials = np.array([np.nan, np.inf, -np.inf, 2.0 ** 31, 2.0 ** 31 + 4096, 3.0e9, -3.0e9, 2147483520.0, 254.5, 255.0, 255.49, 255.5, 256.0,
                          1000.0, 0.5, 1.5, 2.5, 3.5, 127.5, 128.5, -0.5, -1.5, 0.02, 0.019999, 1e-30, 65535.0, 16777216.0, 8388608.0, 8388607.5],
                         np.float32)
+    # huge values whose bit pattern looks like a small integer in the low mantissa byte (0x5700003c = 1.4e14 ...):
+    # the magic-add conversion must not mistake them for in-range results
+    specials = np.concatenate([specials, np.array([0x5700003c, 0x5700007d, 0x60000001, 0x7f000055, 0x4c0000ff, 0x4b8000aa],
+                                                  np.uint32).view(np.float32)])
     ys = rng.integers(0, H, len(specials) * 3)
     xs = rng.integers(0, W, len(specials) * 3)
     img[ys, xs] = np.tile(specials, 3)
