@@ -79,6 +79,7 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     float c = 0.f, s = 0.f;
     if (live) { c = tabCos[a0 + a]; s = tabSin[a0 + a]; }
+    const float inv_c = (c != 0.f) ? __frcp_rn(c) : 0.f;      // only used to predict bin boundaries (then verified)
     const int off = (hc.numrho - 1) / 2 + 1;
     int* row = acc + a * RSS + off;
 #define HOUGH_R(xx) __float2int_rn(__fadd_rn(__fmul_rn((float)(xx), c), ys))
@@ -95,23 +96,34 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
         if (r1 == r2) {
             atomicAdd(&row[r1], __popc(m));
         } else if (abs(r2 - r1) <= 2 && __popc(m) > 4) {
-            // r is monotone in x: locate the (at most two) bin boundaries inside the word by bisection
-            int lo = fb, hi = lb;                       // R(lo) == r1, R(hi) != r1
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (HOUGH_R(x0 + mid) == r1) lo = mid; else hi = mid;
-            }
+            // r is monotone in x: locate the (at most two) bin boundaries inside the word.  The crossing of
+            // r + 0.5 (towards r2) is predicted from the real-valued line x = (r +- 0.5 - y sin) / cos, the exact
+            // float expression is then probed at the prediction and its neighbour (two evaluations instead of a
+            // five-step bisection); whatever interval is left - the prediction can be off by one where OpenCV's
+            // two float roundings matter - is finished by bisection on the exact expression.
+            const float half = (r2 > r1) ? 0.5f : -0.5f;
+            auto last_with = [&](int lo, int hi, int rr) -> int {       // R(lo) == rr, R(hi) != rr  ->  largest x with R(x) == rr
+                const float xg = __fmul_rn(__fsub_rn(__fadd_rn((float)rr, half), ys), inv_c) - (float)x0;
+                int g = min(max(__float2int_rd(xg), lo), hi - 1);
+                if (HOUGH_R(x0 + g) == rr) lo = g; else hi = g;
+                if (hi - lo > 1) {
+                    g = (lo == g) ? g + 1 : g - 1;
+                    if (HOUGH_R(x0 + g) == rr) lo = g; else hi = g;
+                }
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (HOUGH_R(x0 + mid) == rr) lo = mid; else hi = mid;
+                }
+                return lo;
+            };
+            const int lo = last_with(fb, lb, r1), hi = lo + 1;
             int c1 = __popc(m & bit_range(fb, lo));
             atomicAdd(&row[r1], c1);
             int rm = HOUGH_R(x0 + hi);
             if (rm == r2) {
                 atomicAdd(&row[r2], __popc(m & bit_range(hi, lb)));
             } else {
-                int lo2 = hi, hi2 = lb;                 // R(lo2) == rm, R(hi2) == r2
-                while (hi2 - lo2 > 1) {
-                    int mid = (lo2 + hi2) >> 1;
-                    if (HOUGH_R(x0 + mid) == rm) lo2 = mid; else hi2 = mid;
-                }
+                const int lo2 = last_with(hi, lb, rm), hi2 = lo2 + 1;
                 int c2 = __popc(m & bit_range(hi, lo2));
                 if (c2) atomicAdd(&row[rm], c2);
                 atomicAdd(&row[r2], __popc(m & bit_range(hi2, lb)));

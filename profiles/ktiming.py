@@ -45,5 +45,9 @@ print("counters", h.counters())
 tot = sum(acc.values()) / R
 print("total %.3f ms / step of %d frames" % (tot, B))
 for (line, k), ms in acc.items():
-    m = re.search(r"(k_\w+)", src[line - 1]) or re.search(r"(k_\w+)", src[line - 2]) or re.search(r"(k_\w+)", src[line - 3])
+    m = None
+    for back in range(1, 9):                 # the launch (or the macro that holds it) is at most a few lines above
+        m = re.search(r"(k_\w+)", src[line - back])
+        if m:
+            break
     print("%-28s line %4d #%d  %8.1f us  %5.1f%%" % (m.group(1) if m else "?", line, k, 1e3 * ms / R, 100 * ms / R / tot))
