@@ -120,3 +120,41 @@ def test_label_and_edge_invariants_full_frame():
                 assert (er <= equ).all() and (morph >= er).all()
     finally:
         h.close()
+
+
+def test_prep_walks_large_batches_and_ragged_rows():
+    """k_prep keeps at most 16 frames in flight and lets its CTAs walk the rest of the batch; rows whose byte length is
+    not a multiple of the 2 KB TMA stage end in a partial stage.  40 distinct small frames (W = 520: one full and one
+    32-byte stage per row) with blots, star-like pixels and special values: the flipped / clipped / converted planes
+    and the histograms of every frame must equal NumPy's."""
+    from lfd_b200 import _lib
+    H, W, n = 67, 520, 40
+    rng = np.random.default_rng(77)
+    frames = rng.normal(0, 0.03, (n, H, W)).astype(np.float32)
+    frames[rng.random((n, H, W)) < 0.002] += 9.0                           # bytes >= 2: the staged histogram path
+    frames[rng.random((n, H, W)) < 0.0005] = 400.0                         # saturation: the exact conversion path
+    frames[3, 5, 7] = np.nan; frames[17, 60, 519] = np.inf; frames[39, 66, 0] = np.uint32(0x5700003c).view(np.float32)
+    rects = [np.array([[5 + i % 7, 20 + i % 7, 30 + i, 60 + i], [0, 3, 500, 520]], np.int32) for i in range(n)]
+    pb, pd = dict(rp.DEFAULT_BRIGHT), dict(rp.DEFAULT_DIM)
+    h = _lib.Handle(H, W, max_batch=n)
+    try:
+        h.set_params(pb, pd)
+        h.submit(frames, rects, flags=_lib.KEEP_TAPS)
+        h.wait()
+        for f in range(n):
+            img = frames[f].copy()
+            for r0, r1, c0, c1 in rects[f]:
+                img[r0:r1, c0:c1] = 0.0
+            t = img[::-1].copy()
+            with np.errstate(invalid="ignore"):
+                t[t < 0] = 0
+                g0 = rp.cv2.convertScaleAbs(t)
+                t[t < pd["minFlux"]] = 0
+                t[t > 0] += pd["addFlux"]
+                g1 = rp.cv2.convertScaleAbs(t)
+            assert np.array_equal(h.stage(f, 0, "gray"), g0), f
+            assert np.array_equal(h.stage(f, 1, "gray"), g1), f
+            assert np.array_equal(h.stage(f, 0, "hist").astype(np.int64), np.bincount(g0.ravel(), minlength=256)), f
+            assert np.array_equal(h.stage(f, 1, "hist").astype(np.int64), np.bincount(g1.ravel(), minlength=256)), f
+    finally:
+        h.close()
