@@ -18,14 +18,64 @@ import re
 
 import numpy as np
 
-__all__ = ["read", "read_header", "write_image", "write_bintable", "read_raw_image", "FITSHeader"]
+__all__ = ["read", "read_header", "read_columns", "write_image", "write_bintable", "read_raw_image", "read_raw_image_into",
+           "FITSHeader"]
 
 BLOCK = 2880
 CARD = 80
 
 
 class FITSHeader(dict):
-    """Header as a dict keyed by upper-case keyword (enough for ``h['TAI']`` style access)."""
+    """Header as a dict keyed by upper-case keyword (enough for ``h['TAI']`` style access).
+
+    Values read from a file are kept as the raw card text and parsed on first access: a frame header has ~40 cards
+    of which the driver reads a dozen, and parsing is per-frame interpreter time the loader threads serialise on."""
+
+    __slots__ = ("_raw",)
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._raw = set()
+
+    def _set_raw(self, key, text):
+        dict.__setitem__(self, key, text)
+        self._raw.add(key)
+
+    def __setitem__(self, key, value):
+        self._raw.discard(key)
+        dict.__setitem__(self, key, value)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if key in self._raw:
+            v = _parse_value(v)
+            self._raw.discard(key)
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def _all(self):
+        for k in list(self._raw):
+            self[k]
+        return self
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+    def __eq__(self, other):
+        if isinstance(other, FITSHeader):
+            other._all()
+        return dict.__eq__(self._all(), other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return dict.__repr__(self._all())
 
 
 def _parse_value(raw):
@@ -70,16 +120,16 @@ def _read_header_at(f):
         if len(block) < BLOCK:
             raise EOFError("truncated FITS header")
         nread += BLOCK
+        text = block.decode("ascii", errors="replace")
         for i in range(0, BLOCK, CARD):
-            card = block[i:i + CARD].decode("ascii", errors="replace")
-            key = card[:8].strip()
+            key = text[i:i + 8].strip()
             if key == "END":
                 done = True
                 break
-            if not key or key in ("COMMENT", "HISTORY"):
+            if not key or key == "COMMENT" or key == "HISTORY":
                 continue
-            if card[8:10] == "= ":
-                hdr[key] = _parse_value(card[10:])
+            if text[i + 8:i + 10] == "= ":
+                hdr._set_raw(key, text[i + 10:i + CARD])
     return hdr, nread
 
 
@@ -105,7 +155,19 @@ _TFORM_RE = re.compile(r"^(\d*)([LXBIJKAEDCMPQ])")
 _TFORM_DTYPE = {"B": "u1", "I": ">i2", "J": ">i4", "K": ">i8", "E": ">f4", "D": ">f8", "L": "u1"}
 
 
+_dtype_cache = {}
+
+
 def _table_dtype(h):
+    raw = dict.__getitem__              # the unparsed card text is as good a cache key as the parsed value
+    key = tuple((raw(h, "TTYPE%d" % i), raw(h, "TFORM%d" % i)) for i in range(1, h["TFIELDS"] + 1))
+    dt = _dtype_cache.get(key)
+    if dt is None:
+        dt = _dtype_cache[key] = _build_table_dtype(h)
+    return dt
+
+
+def _build_table_dtype(h):
     fields = []
     for i in range(1, h["TFIELDS"] + 1):
         name = h["TTYPE%d" % i]
@@ -133,24 +195,35 @@ def _native(arr):
     return arr.astype(arr.dtype.newbyteorder("="))
 
 
+def _iter_hdus_f(f):
+    """(header, data offset, data bytes) of every HDU of the open file ``f``; the caller may seek between items."""
+    size = os.fstat(f.fileno()).st_size
+    pos = 0
+    while pos < size:
+        f.seek(pos)
+        try:
+            h, nh = _read_header_at(f)
+        except EOFError:
+            return
+        nbytes = _data_nbytes(h)
+        pos += nh
+        yield h, pos, nbytes
+        pos += _pad(nbytes)
+
+
 def _iter_hdus(path):
     with open(path, "rb") as f:
-        size = os.fstat(f.fileno()).st_size
-        while f.tell() < size:
-            try:
-                h, _ = _read_header_at(f)
-            except EOFError:
-                return
-            nbytes = _data_nbytes(h)
-            pos = f.tell()
-            yield h, pos, nbytes
-            f.seek(pos + _pad(nbytes))
+        yield from _iter_hdus_f(f)
 
 
-def _read_hdu(path, h, pos, nbytes):
+def _read_hdu(path, h, pos, nbytes, f=None):
     if nbytes == 0:
         return None
-    with open(path, "rb") as f:
+    if f is None:
+        with open(path, "rb") as f2:
+            f2.seek(pos)
+            buf = f2.read(nbytes)
+    else:
         f.seek(pos)
         buf = f.read(nbytes)
     if h.get("XTENSION", "").strip() == "BINTABLE":
@@ -175,22 +248,46 @@ def read(path, ext=None, header=False):
 
     ``header`` truthy (the reference passes the *string* ``"True"``) returns ``(data, header)``.
     """
-    hdus = list(_iter_hdus(path))
-    if ext is None:
-        pick = None
-        for i, (h, pos, nbytes) in enumerate(hdus):
-            if nbytes > 0:
-                pick = i
+    with open(path, "rb") as f:
+        found = None
+        for i, (h, pos, nbytes) in enumerate(_iter_hdus_f(f)):
+            if (ext is None and nbytes > 0) or (ext is not None and i == ext):
+                found = (h, pos, nbytes)
                 break
-        if pick is None:
-            raise OSError("No extensions have data")
-    else:
-        pick = ext
-    h, pos, nbytes = hdus[pick]
-    data = _read_hdu(path, h, pos, nbytes)
+        if found is None:
+            if ext is None:
+                raise OSError("No extensions have data")
+            raise IndexError("list index out of range")
+        h, pos, nbytes = found
+        data = _read_hdu(path, h, pos, nbytes, f)
     if header:
         return data, h
     return data
+
+
+def read_columns(path, names):
+    """Selected columns of the first binary-table HDU as native-endian arrays ({name: array}) - what the catalog
+    filter needs (removestars.py:97-104) without converting the other columns of a photoObj table (hundreds in the
+    real files).  Raises KeyError for a missing column like the recarray access would."""
+    with open(path, "rb") as f:
+        for h, pos, nbytes in _iter_hdus_f(f):
+            if nbytes == 0:
+                continue
+            if h.get("XTENSION", "").strip() != "BINTABLE":
+                raise ValueError("first HDU with data is not a binary table")
+            dt = _table_dtype(h)
+            if dt.itemsize != h["NAXIS1"]:
+                raise ValueError("row size mismatch: dtype %d vs NAXIS1 %d" % (dt.itemsize, h["NAXIS1"]))
+            f.seek(pos)
+            arr = np.frombuffer(f.read(nbytes), dtype=dt, count=h["NAXIS2"])
+            out = {}
+            for k in names:
+                if k not in dt.fields:
+                    raise KeyError(k)
+                col = arr[k]
+                out[k] = col.astype(col.dtype.newbyteorder("="))
+            return out
+    raise OSError("No extensions have data")
 
 
 def read_header(path, ext=0):
@@ -224,14 +321,14 @@ def read_raw_image_into(path, dest):
     """Like read_raw_image, but the payload is read straight into ``dest`` (a writable C-contiguous uint32 array of
     shape (NAXIS2, NAXIS1), e.g. a slot of the library's pinned staging) with ``readinto`` - no intermediate copy and
     no GIL while the bytes move.  Returns the header; raises ValueError if the image does not fit ``dest``."""
-    for h, pos, nbytes in _iter_hdus(path):
-        if nbytes == 0:
-            continue
-        if h["BITPIX"] != -32 or h["NAXIS"] != 2:
-            raise ValueError("raw upload path needs a 2-D BITPIX=-32 image")
-        if (h["NAXIS2"], h["NAXIS1"]) != tuple(dest.shape) or dest.dtype.itemsize != 4:
-            raise ValueError("image shape %s does not match the staging slot %s" % ((h["NAXIS2"], h["NAXIS1"]), dest.shape))
-        with open(path, "rb", buffering=0) as f:
+    with open(path, "rb", buffering=0) as f:
+        for h, pos, nbytes in _iter_hdus_f(f):
+            if nbytes == 0:
+                continue
+            if h["BITPIX"] != -32 or h["NAXIS"] != 2:
+                raise ValueError("raw upload path needs a 2-D BITPIX=-32 image")
+            if (h["NAXIS2"], h["NAXIS1"]) != tuple(dest.shape) or dest.dtype.itemsize != 4:
+                raise ValueError("image shape %s does not match the staging slot %s" % ((h["NAXIS2"], h["NAXIS1"]), dest.shape))
             f.seek(pos)
             mv = memoryview(dest).cast("B")
             got = 0
@@ -240,7 +337,7 @@ def read_raw_image_into(path, dest):
                 if not k:
                     raise OSError("short read in %s" % path)
                 got += k
-        return h
+            return h
     raise OSError("no image HDU in %s" % path)
 
 

@@ -23,9 +23,11 @@ _BANDS = ("u", "g", "r", "i", "z")
 
 def read_photoObj_arrays(path_to_photoOBJ):
     """The eight columns removestars.py:97-104 reads, as arrays."""
+    cols = ("OBJC_TYPE", "TYPE", "ROWC", "COLC", "PETROTH90", "PSFMAG", "NOBSERVE", "NDETECT")
+    if hasattr(fitsio, "read_columns"):          # fitsio_lite: converts only these columns
+        return fitsio.read_columns(path_to_photoOBJ, cols)
     data, _hdr = fitsio.read(path_to_photoOBJ, header="True")
-    return {k: np.asarray(data[k]) for k in
-            ("OBJC_TYPE", "TYPE", "ROWC", "COLC", "PETROTH90", "PSFMAG", "NOBSERVE", "NDETECT")}
+    return {k: np.asarray(data[k]) for k in cols}
 
 
 def _ceil_int(a):
@@ -56,33 +58,32 @@ def star_rects(cat, _filter, shape, defaultxy, filter_caps, maxxy, pixscale, mag
     goes negative wrap to an empty slice exactly like NumPy's indexing does."""
     b = _BANDS.index(_filter)
     H, W = shape
-    rows = _ceil_int(cat["ROWC"]); cols = _ceil_int(cat["COLC"])
-    mags = _ceil_int(cat["PSFMAG"]); p90 = _ceil_int(cat["PETROTH90"])
-    n = len(rows)
+    n = len(cat["ROWC"])
     if n == 0:
         return np.zeros((0, 4), np.int32)
+    # one ceil over the four (n, 5) columns (math.ceil of every band of every object, removestars.py:113-130:
+    # a non-finite value anywhere raises, whatever the filter)
+    c = _ceil_int(np.stack([cat["ROWC"], cat["COLC"], cat["PSFMAG"], cat["PETROTH90"]]))
+    rows, cols, mags, p90 = c[0][:, b], c[1][:, b], c[2], c[3][:, b]
     keep = mags[:, b] < filter_caps[_filter]
-    big = np.zeros(n, np.int64)
-    for j in range(5):
-        for k in range(j + 1, 5):
-            big += np.abs(mags[:, j] - mags[:, k]) > maxmagdiff
+    big = (np.abs(mags[:, _PAIR_J] - mags[:, _PAIR_K]) > maxmagdiff).sum(axis=1)      # the 10 band pairs (:217-224)
     keep &= magcount >= big
     keep &= np.asarray(cat["NOBSERVE"]) == np.asarray(cat["NDETECT"])
     dxy = np.full(n, defaultxy, np.int64)
-    pos = p90[:, b] > 0
-    dxy[pos] = (p90[pos, b] / pixscale).astype(np.int64) + 10     # int() truncation of a positive float
+    pos = p90 > 0
+    dxy[pos] = (p90[pos] / pixscale).astype(np.int64) + 10     # int() truncation of a positive float
     dxy[dxy > maxxy] = defaultxy
-    x, y = cols[keep, b], rows[keep, b]
-    dk = dxy[keep]
+    x, y, dk = cols[keep], rows[keep], dxy[keep]
+    # slice.indices() for step 1: a negative bound counts from the end, then both are clamped to [0, length]
+    r = np.stack([x - dk, x + dk])
+    r = np.clip(np.where(r < 0, r + H, r), 0, H)
+    cc = np.stack([y - dk, y + dk])
+    cc = np.clip(np.where(cc < 0, cc + W, cc), 0, W)
+    ok = (r[0] < r[1]) & (cc[0] < cc[1])
+    return np.stack([r[0][ok], r[1][ok], cc[0][ok], cc[1][ok]], axis=1).astype(np.int32).reshape(-1, 4)
 
-    def resolve(v, length):
-        # slice.indices() for step 1: a negative bound counts from the end, then both are clamped to [0, length]
-        return np.clip(np.where(v < 0, v + length, v), 0, length)
 
-    r0, r1 = resolve(x - dk, H), resolve(x + dk, H)
-    c0, c1 = resolve(y - dk, W), resolve(y + dk, W)
-    ok = (r0 < r1) & (c0 < c1)
-    return np.stack([r0[ok], r1[ok], c0[ok], c1[ok]], axis=1).astype(np.int32).reshape(-1, 4)
+_PAIR_J, _PAIR_K = (np.array(v) for v in zip(*[(j, k) for j in range(5) for k in range(j + 1, 5)]))
 
 
 def remove_stars(img, _run, _camcol, _filter, _field, defaultxy, filter_caps, maxxy, pixscale, magcount,

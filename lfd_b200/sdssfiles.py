@@ -15,6 +15,7 @@ _PATTERNS = {
 }
 _FILTERS = "ugriz"
 _runlist_cache = {}
+_rerun_cache = {}
 
 
 def runlist(reload=False):
@@ -35,10 +36,19 @@ def runlist(reload=False):
     # the reference drops the duplicate bad entry for run 5194 (sdss/files.py:668-670)
     rl = rl[(rl["run"] != 5194) | (rl["rerun"] == b"301")]
     _runlist_cache[path] = rl
+    _rerun_cache.clear()
     return rl
 
 
 def find_rerun(run):
+    key = (os.environ.get("PHOTO_REDUX"), run)
+    r = _rerun_cache.get(key)
+    if r is None:
+        r = _rerun_cache[key] = _find_rerun(run)
+    return r
+
+
+def _find_rerun(run):
     rl = runlist()
     w, = np.where(rl["run"] == run)
     if w.size == 0:
