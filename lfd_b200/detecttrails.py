@@ -19,7 +19,7 @@ import numpy as _np
 
 from . import _lib, sdssfiles as files
 from .processfield import result_from_device, setup_debug
-from .removestars import read_photoObj_arrays, star_rects
+from .removestars import read_photoObj_arrays, star_rects, star_rects_batch
 
 try:
     import fitsio
@@ -121,10 +121,11 @@ def _results_prefix(run, camcol, filter, field, h):
             "{h['CD1_2']} {h['CD2_1']} {h['CD2_2']} ")
 
 
-def _load_one(frame, params_removestars, slot=None):
+def _load_one(frame, params_removestars, slot=None, want_rects=True):
     """Host side of one frame (runs in a loader thread): FITS image + header line prefix, photoObj catalog -> blot
     rectangles.  With ``slot`` (a row of a handle's pinned staging viewed as uint32) an uncompressed frame of that
-    shape is read straight into it as raw big-endian payload.
+    shape is read straight into it as raw big-endian payload.  With ``want_rects=False`` the catalog columns are
+    returned in place of the rectangles (the driver resolves a whole batch at once, star_rects_batch).
     Returns ("staged", None, True, rects, printit) | ("ok", pixels, big_endian, rects, printit) | ("err", exc)."""
     run, camcol, filter, field = frame
     try:
@@ -142,12 +143,31 @@ def _load_one(frame, params_removestars, slot=None):
             img, printit, big_endian = _load_frame(run, camcol, filter, field, raw=True)
         cat = read_photoObj_arrays(files.filename("photoObj", run=run, camcol=camcol, field=field))
         shape = slot.shape if staged else img.shape
-        rects = star_rects(cat, filter, shape, **dict(params_removestars))
+        rects = star_rects(cat, filter, shape, **dict(params_removestars)) if want_rects else cat
         if staged:
             return ("staged", None, True, rects, printit)
         return ("ok", img, big_endian, rects, printit)
     except Exception as e:   # noqa: BLE001 - the reference swallows everything per frame
         return ("err", e)
+
+
+def _resolve_rects(loaded, chunk, shape0, params_removestars):
+    """Replace the catalog columns the loaders returned by blot rectangles: one vectorised call for the frames of
+    the batch that share the common frame shape, frame by frame for the others."""
+    loaded = list(loaded)
+    pr = dict(params_removestars)
+    group = [j for j, it in enumerate(loaded) if it[0] == "staged" or (it[0] == "ok" and it[1].shape == shape0)]
+    if group:
+        res = star_rects_batch([loaded[j][3] for j in group], [chunk[j][2] for j in group], shape0, **pr)
+        for j, r in zip(group, res):
+            loaded[j] = ("err", r) if isinstance(r, BaseException) else loaded[j][:3] + (r,) + loaded[j][4:]
+    for j, it in enumerate(loaded):
+        if it[0] == "ok" and j not in group:
+            try:
+                loaded[j] = it[:3] + (star_rects(it[3], chunk[j][2], it[1].shape, **pr),) + it[4:]
+            except Exception as e:   # noqa: BLE001
+                loaded[j] = ("err", e)
+    return loaded
 
 
 _handles = {}
@@ -254,14 +274,14 @@ def compute_fields(frames, params_bright, params_dim, params_removestars, batch=
             if h is not None:
                 release(h)                                   # its previous batch (ci - N_RING) is long done
                 st = h.host_frames.view(_np.uint32)
-                futs[ci] = [pool.submit(_load_one, fr, params_removestars, st[j]) for j, fr in enumerate(chunks[ci])]
+                futs[ci] = [pool.submit(_load_one, fr, params_removestars, st[j], False) for j, fr in enumerate(chunks[ci])]
             else:
-                futs[ci] = [pool.submit(_load_one, fr, params_removestars, None) for fr in chunks[ci]]
+                futs[ci] = [pool.submit(_load_one, fr, params_removestars, None, False) for fr in chunks[ci]]
 
         prefetch(0)
         for ci, chunk in enumerate(chunks):
             prefetch(ci + 1)
-            loaded = [f.result() for f in futs.pop(ci)]
+            loaded = _resolve_rects([f.result() for f in futs.pop(ci)], chunk, shape0, params_removestars)
             base = ci * batch
             for j, item in enumerate(loaded):
                 loaded_all[base + j] = item

@@ -155,3 +155,31 @@ def test_check_theta_matches_oracle():
         if rng.random() < 0.5:
             h2[:, 0, :] = h1[:1, 0, :] + rng.normal(0, 0.05, (n2, 2)).astype(np.float32)
         assert lfd_b200.check_theta(h1, h2, 3, 25, 0.15, 0.15, False) == rp.check_theta(h1, h2, 3, 25, 0.15, 0.15)
+
+
+def test_star_rects_batch_equals_per_frame():
+    """The batched catalog filter (one set of NumPy calls per GPU batch) returns exactly the per-frame rectangles,
+    for mixed filters, an empty catalog and a catalog with a NaN (which only fails its own frame)."""
+    from lfd_b200.removestars import star_rects_batch
+    cats, flts = [], []
+    for i, flt in enumerate("ugrizrg"):
+        _img, cat = synth.make_case("dense" if i % 3 == 0 else "sparse", 70 + i)
+        cats.append(cat); flts.append(flt)
+    empty = {k: np.asarray(v)[:0] for k, v in cats[0].items()}
+    bad = {k: np.array(v, copy=True) for k, v in cats[1].items()}
+    bad["PSFMAG"] = bad["PSFMAG"].astype(np.float32); bad["PSFMAG"][3, 2] = np.nan
+    exc = OSError("unreadable photoObj")
+    for batch, fl in ((cats, flts), (cats[:2] + [empty] + cats[2:], flts[:2] + ["r"] + flts[2:]),
+                      (cats[:3] + [bad, exc] + cats[3:], flts[:3] + ["i", "z"] + flts[3:])):
+        got = star_rects_batch(batch, fl, (1489, 2048), **rp.DEFAULT_REMOVESTARS)
+        assert len(got) == len(batch)
+        for c, f, g in zip(batch, fl, got):
+            if isinstance(c, BaseException):
+                assert g is c
+                continue
+            try:
+                ref = star_rects(c, f, (1489, 2048), **rp.DEFAULT_REMOVESTARS)
+            except Exception as e:   # noqa: BLE001
+                assert type(g) is type(e) and str(g) == str(e)
+                continue
+            assert g.dtype == np.int32 and np.array_equal(g, ref)
