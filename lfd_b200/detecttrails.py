@@ -263,7 +263,7 @@ def compute_fields(frames, params_bright, params_dim, params_removestars, batch=
             for g in gidx:
                 outcome[g] = ("err", e)
 
-    nload = loaders or max(2, min(8, (os.cpu_count() or 2)))
+    nload = loaders or int(os.environ.get("LFD_LOADER_THREADS", 0)) or max(2, min(8, (os.cpu_count() or 2)))
     with ThreadPoolExecutor(max_workers=nload) as pool:
         futs = {}
 
