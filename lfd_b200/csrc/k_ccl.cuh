@@ -228,7 +228,11 @@ __device__ __forceinline__ void suf_union(int* p, int a, int b)
 #define CCL_BAND_CAP 1536          // runs of one band kept in shared memory (12 B each = 18 KB)
 
 // dynamic shared memory of k_ccl_band: CCL_BAND rows of mask words, then the band's parents and runs
-__host__ __device__ inline size_t ccl_band_smem(int WW) { return (size_t)CCL_BAND * WW * 4 + (size_t)CCL_BAND_CAP * 12; }
+// (+ the band's per-word run-rank prefixes, u16, and its CCL_BAND + 1 row bases)
+__host__ __device__ inline size_t ccl_band_smem(int WW)
+{
+    return (size_t)CCL_BAND * WW * 4 + (size_t)CCL_BAND_CAP * 12 + (size_t)(CCL_BAND + 2) * 4 + (size_t)CCL_BAND * WW * 2;
+}
 
 // 3+4a fused: materialise the runs of a CCL_BAND-row band, link all of its row pairs at once with a
 // union-find that lives in shared memory, and publish band-local roots.  Run ids are raster-ordered, so
@@ -252,17 +256,39 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     u32* sw = band_sm;                                        // [CCL_BAND][WW]
     int* sp = (int*)(band_sm + CCL_BAND * d.WW);              // [CCL_BAND_CAP]
     Run* srun = (Run*)(sp + CCL_BAND_CAP);                    // [CCL_BAND_CAP]
+    int* srb = (int*)(srun + CCL_BAND_CAP);                   // [CCL_BAND + 2] row bases of rows y0 .. y1
+    u16* swp = (u16*)(srb + CCL_BAND + 2);                    // [CCL_BAND][WW] run-rank prefix of every mask word
     const bool insm = nb <= CCL_BAND_CAP;
     const int WW = d.WW;
-    for (int i = threadIdx.x; i < (y1 - y0) * WW; i += blockDim.x) {
-        int yy = i / WW, w = i - yy * WW;
-        u32 v = m[(size_t)(y0 + yy) * WW + w];
-        sw[i] = kind ? (~v & tail_mask(w, d.W)) : v;
+    {
+        // stage the band: its mask rows and prefix words are contiguous in global memory; four independent loads per
+        // thread and iteration (this loop used to be one dependent load -> store per iteration: 12 % of the samples)
+        const int tot = (y1 - y0) * WW;
+        const u32* src = m + (size_t)y0 * WW;
+        const u16* psrc = b.wpre + (size_t)y0 * WW;
+        for (int i0 = threadIdx.x; i0 < tot; i0 += 4 * blockDim.x) {
+            u32 v[4]; u16 pw[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * blockDim.x;
+                v[k] = i < tot ? src[i] : 0u;
+                pw[k] = i < tot ? psrc[i] : (u16)0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * blockDim.x;
+                if (i < tot) { sw[i] = kind ? ~v[k] : v[k]; swp[i] = pw[k]; }
+            }
+        }
+        if (threadIdx.x <= y1 - y0) srb[threadIdx.x] = b.rowbase[y0 + threadIdx.x];
+        __syncthreads();
+        if (kind && (d.W & 31))                               // complemented rows: clear the bits past the frame edge
+            for (int yy = threadIdx.x; yy < y1 - y0; yy += blockDim.x) sw[yy * WW + WW - 1] &= tail_mask(WW - 1, d.W);
     }
     __syncthreads();
     // fill: one warp per row, rows strided over the 8 warps
     for (int y = y0 + (threadIdx.x >> 5); y < y1; y += 8) {
-        int rb = b.rowbase[y];
+        int rb = srb[y - y0];
         const u32* row = sw + (y - y0) * WW;
         // words that are not all-ones, one ballot per 32-word chunk (W <= 4096 -> at most 4 chunks): a run
         // that leaves its word ends in the next such word, found with a bit scan instead of a serial walk
@@ -277,7 +303,7 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
             u32 cur = row[w], prev = w ? row[w - 1] : 0u;
             u32 starts = cur & ~((cur << 1) | (prev >> 31));
             if (!starts) continue;
-            int id = rb + b.wpre[(size_t)y * WW + w];
+            int id = rb + swp[(y - y0) * WW + w];
             while (starts) {
                 int s = __ffs(starts) - 1;
                 starts &= starts - 1;
@@ -331,7 +357,7 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
                     u32 cur = row[w], prev = w ? row[w - 1] : 0u;
                     u32 starts = cur & ~((cur << 1) | (prev >> 31));
                     u32 upto = (bit == 31) ? 0xffffffffu : ((2u << bit) - 1u);
-                    j = b.rowbase[yy] + b.wpre[(size_t)yy * WW + w] + __popc(starts & upto) - 1;
+                    j = srb[yy - y0] + swp[(yy - y0) * WW + w] + __popc(starts & upto) - 1;
                     break;
                 }
             }

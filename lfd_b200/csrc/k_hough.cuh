@@ -48,6 +48,8 @@ k_hough_compact(const u32* __restrict__ nzmask, const u32* __restrict__ boxmask,
 
 #define HOUGH_THREADS 256
 
+#define HOUGH_MIN_SEGS 512
+
 // smem accumulator row stride: odd, so that lanes (= angles) voting for similar rho hit different banks
 __host__ __device__ inline int hough_rss(int RS) { return RS | 1; }
 
@@ -63,7 +65,11 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     int nseg = ctl[f].nseg[which];
     // lanes = angles; when apc < 32 the warp covers 32/apc segments at once
     const int per = (hc.apc >= 32) ? 1 : (32 / hc.apc);
-    if (blockIdx.x * (HOUGH_THREADS / 32) * per >= nseg) return;          // no segment for any warp of this CTA
+    // Every CTA zeroes and flushes apc x RSS accumulator cells whatever it votes, so a frame gets only as many of
+    // the gridDim.x CTAs as its segment list can keep busy (>= HOUGH_MIN_SEGS each): the box image has ~10x fewer
+    // segments than the morphology output
+    const int nchunks = min((int)gridDim.x, max(1, (nseg + HOUGH_MIN_SEGS - 1) / HOUGH_MIN_SEGS));
+    if ((int)blockIdx.x >= nchunks || nseg == 0) return;
     const int RSS = hough_rss(hc.RS);
     int g = blockIdx.y;
     int a0 = g * hc.apc;
@@ -76,7 +82,7 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     bool live = (per == 1) ? (lane < na) : (sub < per && a < na);
     if (per == 1) { sub = 0; a = lane; }
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int nwarps = (nchunks * blockDim.x) >> 5;
     float c = 0.f, s = 0.f;
     if (live) { c = tabCos[a0 + a]; s = tabSin[a0 + a]; }
     const float inv_c = (c != 0.f) ? __frcp_rn(c) : 0.f;      // only used to predict bin boundaries (then verified)
@@ -144,11 +150,12 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
 #undef HOUGH_R
     __syncthreads();
     int* gacc = accum + ((size_t)f * 2 + which) * accum_stride;
-    for (int i = threadIdx.x; i < na * RSS; i += blockDim.x) {
-        int v = acc[i];
-        if (v) {
-            int aa = i / RSS, col = i - aa * RSS;
-            atomicAdd(&gacc[(size_t)(a0 + aa + 1) * hc.RS + col], v);
+    for (int aa = threadIdx.x >> 5; aa < na; aa += HOUGH_THREADS / 32) {        // one warp per angle row: no division
+        const int* arow = acc + aa * RSS;
+        int* grow = gacc + (size_t)(a0 + aa + 1) * hc.RS;
+        for (int col = lane; col < RSS; col += 32) {
+            const int v = arow[col];
+            if (v) atomicAdd(&grow[col], v);
         }
     }
 }
