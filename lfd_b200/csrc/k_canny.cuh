@@ -169,9 +169,11 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
         const int wa = max(mw0 - 1, 0), wb = min(mw0 + 7, d.WW - 1);
         const int nw = wb - wa + 1, tot = (rb - ra + 1) * nw;
         u32 any = 0;
-        for (int i = lane; i < tot; i += 32) {
-            int yy = ra + i / nw, w = wa + i % nw;
-            any |= nz[(size_t)f * d.NW + (size_t)yy * d.WW + w];
+        const u32* nzf = nz + (size_t)f * d.NW + wa;
+        if (nw == 9) {                                      // interior strips: constant divisor (mul-shift, no division)
+            for (int i = lane; i < tot; i += 32) any |= nzf[(ra + i / 9) * d.WW + i % 9];
+        } else {
+            for (int i = lane; i < tot; i += 32) any |= nzf[(ra + i / nw) * d.WW + i % nw];
         }
         if (!__any_sync(FULLMASK, any != 0)) {
             for (int y = y0; y < y1; y++) {

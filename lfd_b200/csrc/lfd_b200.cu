@@ -635,7 +635,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     const bool taps = flags & LFD_KEEP_TAPS;
     const int tbase = 2 + pass * (T_PER_PASS - 1);   // event index preceding this pass's first stage
     HoughBufs& hb = h->hb[pass];
-    dim3 rows((d.H + CCL_WARPS - 1) / CCL_WARPS, n);
+    dim3 rows((d.H + CCL_WARPS * CCL_RC_ROWS - 1) / (CCL_WARPS * CCL_RC_ROWS), n);
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
@@ -1161,7 +1161,7 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
         k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d, low, high);
     }
     LAUNCH_CHECK();
-    dim3 rows((d.H + CCL_WARPS - 1) / CCL_WARPS, n);
+    dim3 rows((d.H + CCL_WARPS * CCL_RC_ROWS - 1) / (CCL_WARPS * CCL_RC_ROWS), n);
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(h->cand[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
