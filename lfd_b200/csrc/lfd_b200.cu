@@ -731,7 +731,8 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     int* const v_accum = hb.accum + (size_t)f0 * 2 * hb.accum_stride;
     u64* const v_keys = hb.keys + (size_t)f0 * 2 * hb.key_stride;
     CK(cudaMemsetAsync(v_accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
-    k_hough_compact<<<dim3(32, n, 2), 256, 0, s>>>(v_nz, v_box, v_segs, C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
+    // a thread's iterations are a serial chain (load -> ballot -> slot atomic -> store): many CTAs, few iterations each
+    k_hough_compact<<<dim3(128, n, 2), 256, 0, s>>>(v_nz, v_box, v_segs, C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
     k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(v_segs, v_accum, hb.tabSin, hb.tabCos, C, pass,
                                                                             hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
     int cells = hb.hc.numangle * hb.hc.numrho;
