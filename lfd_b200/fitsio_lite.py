@@ -64,6 +64,11 @@ class FITSHeader(dict):
     def items(self):
         return dict.items(self._all())
 
+    def copy(self):
+        h = FITSHeader()
+        dict.update(h, self._all())
+        return h
+
     def values(self):
         return dict.values(self._all())
 

@@ -183,3 +183,32 @@ def test_star_rects_batch_equals_per_frame():
                 assert type(g) is type(e) and str(g) == str(e)
                 continue
             assert g.dtype == np.int32 and np.array_equal(g, ref)
+
+
+def test_fitsio_lite_lazy_header_and_column_reader(tmp_path):
+    """Header values are parsed on first access (same values as an eager parse, whatever the access path), and
+    read_columns returns exactly the columns fitsio-style ``read`` returns, native-endian."""
+    img = np.zeros((8, 12), np.float32)
+    p = str(tmp_path / "a.fits")
+    fitsio_lite.write_image(p, img, dict(synth.DEFAULT_HEADER))
+    h = fitsio_lite.read_header(p)
+    eager = {k: fitsio_lite._parse_value(dict.__getitem__(h, k)) if k in h._raw else dict.__getitem__(h, k) for k in list(h.keys())}
+    assert h.get("NOSUCHKEY", 7) == 7 and "TAI" in h and "NOSUCHKEY" not in h
+    assert h.get("CRPIX1") == eager["CRPIX1"] and isinstance(h["NAXIS1"], int) and h["SIMPLE"] is True
+    assert dict(h.items()) == eager and h == eager and h.copy() == eager and list(h.values()) == list(eager.values())
+    h["TAI"] = 1.5                                   # assignment of a real value is not re-parsed
+    assert h["TAI"] == 1.5
+    with pytest.raises(KeyError):
+        h["NOSUCHKEY"]
+    _img, cat = synth.make_case("sparse", 6)
+    q = str(tmp_path / "b.fits")
+    fitsio_lite.write_bintable(q, cat)
+    data = fitsio_lite.read(q)
+    cols = fitsio_lite.read_columns(q, ("ROWC", "PSFMAG", "NOBSERVE"))
+    assert set(cols) == {"ROWC", "PSFMAG", "NOBSERVE"}
+    for k, v in cols.items():
+        assert v.dtype.isnative and v.dtype == data[k].dtype and np.array_equal(v, data[k]), k
+    with pytest.raises(KeyError):
+        fitsio_lite.read_columns(q, ("ROWC", "NOSUCHCOLUMN"))
+    with pytest.raises(ValueError):
+        fitsio_lite.read_columns(p, ("ROWC",))      # an image HDU, not a table
