@@ -223,6 +223,24 @@ int lfd_timer_mark(lfd_handle* h, int slot);
 int lfd_timer_elapsed(lfd_handle* h, int slot_start, lfd_handle* h_end, int slot_end, float* ms);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lfd_kernel_launches(const lfd_handle* h);
+
+/* ---- host-side ingest (plain C++, no GPU needed; the GIL is released by ctypes for the whole call) -------------
+ * lfd_fits_load_frame: fitsio.read + fitsio.read_header of a frame file (lfd/detecttrails/detecttrails.py:113-114).
+ * The first HDU with data must be a 2-D BITPIX=-32 image of height x width without BSCALE/BZERO; its raw big-endian
+ * payload is read into dest (height*width*4 bytes, e.g. a slot of lfd_host_frames; submit with
+ * LFD_INPUT_BIGENDIAN) and the raw value text of the nkeys header cards keys[i] is copied to values + 72*i
+ * (NUL-terminated).  LFD_E_UNSUPPORTED for any other layout or a missing card, LFD_E_ARG for I/O errors: the caller
+ * then uses its general reader, which raises what the reference raises. */
+int lfd_fits_load_frame(const char* path, void* dest, int height, int width, const char* const* keys, int nkeys,
+                        char* values);
+/* lfd_catalog_rects: read_photoObj + the object filter + the blot slices of remove_stars
+ * (lfd/detecttrails/removestars.py:96-130, 212-231) for band (0..4 = ugriz) of one photoObj file: writes the
+ * (row_start, row_stop, col_start, col_stop) rectangles lfd_submit takes, in catalog order.  cap = filter_caps[filter].
+ * LFD_E_UNSUPPORTED when the table is not the plain photoObj layout (ROWC, COLC, PSFMAG, PETROTH90 as 5E, NOBSERVE,
+ * NDETECT as J) or holds a non-finite value (the reference raises there), LFD_E_CAPACITY when max_rects is too small. */
+int lfd_catalog_rects(const char* path, int band, int height, int width, double cap, double maxmagdiff,
+                      double magcount, double pixscale, long long defaultxy, double maxxy, int32_t* rects,
+                      int max_rects, int* n_rects);
 /* Work counters of the last run, summed over the batch: [0] nonzero px voted equ, [1] box, [2] votes,
  * [3] runs fg, [4] runs bg, [5] contours, [6] passing rects, [7] frames that ran dim, [8] frames that ran Hough. */
 int lfd_get_counters(lfd_handle* h, int64_t* out, int n);

@@ -124,10 +124,52 @@ def lib():
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_elapsed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        L.lfd_fits_load_frame.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_char_p]
+        L.lfd_catalog_rects.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_longlong,
+                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         if L.lfd_abi_version() != 1:
             raise ImportError("liblfd_b200.so ABI mismatch")
         _lib = L
     return _lib
+
+
+# ---- host-side ingest in native code (include/lfd_b200.h: lfd_fits_load_frame, lfd_catalog_rects) ------------------
+HEADER_KEYS = ("TAI", "CRPIX1", "CRPIX2", "CRVAL1", "CRVAL2", "CD1_1", "CD1_2", "CD2_1", "CD2_2")   # detecttrails.py:115-117
+_KEYS_C = (ctypes.c_char_p * len(HEADER_KEYS))(*[k.encode() for k in HEADER_KEYS])
+_BANDS = "ugriz"
+
+
+def fits_load_frame(path, slot):
+    """Raw big-endian payload of a plain float32 frame file -> ``slot`` (a C-contiguous (H, W) 4-byte array, e.g. a row
+    of a handle's pinned staging); returns {key: raw card value text} for HEADER_KEYS, or None when the file is not
+    of that plain kind (the caller then uses the general Python reader).  The GIL is released for the whole call."""
+    vals = ctypes.create_string_buffer(72 * len(HEADER_KEYS))
+    rc = lib().lfd_fits_load_frame(os.fsencode(path), slot.ctypes.data_as(ctypes.c_void_p), slot.shape[0], slot.shape[1],
+                                   _KEYS_C, len(HEADER_KEYS), vals)
+    if rc != LFD_OK:
+        return None
+    raw = vals.raw
+    return {k: raw[72 * i:72 * i + 72].split(b"\0", 1)[0].decode("ascii", errors="replace") for i, k in enumerate(HEADER_KEYS)}
+
+
+def catalog_rects(path, _filter, shape, defaultxy, filter_caps, maxxy, pixscale, magcount, maxmagdiff, debug=False):
+    """Blot rectangles of one photoObj file, filter and slice rules of ``removestars.star_rects`` in native code; None
+    when the table is not the plain photoObj layout or needs the Python path's exceptions (non-finite values)."""
+    try:
+        band = _BANDS.index(_filter)
+        args = (float(filter_caps[_filter]), float(maxmagdiff), float(magcount), float(pixscale), int(defaultxy), float(maxxy))
+        cap = max(os.path.getsize(path) // 88 + 1, 1)          # a row holds at least the six columns (4 x 20 + 2 x 4 bytes)
+    except (ValueError, TypeError, KeyError, OverflowError, OSError):
+        return None
+    out = np.empty((cap, 4), np.int32)
+    n = ctypes.c_int(0)
+    rc = lib().lfd_catalog_rects(os.fsencode(path), band, int(shape[0]), int(shape[1]), args[0], args[1], args[2], args[3],
+                                 args[4], args[5], out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n))
+    if rc != LFD_OK:
+        return None
+    return out[:n.value].copy() if n.value * 4 < cap else out[:n.value]
 
 
 def _kernel_hw(kernel, name):

@@ -21,6 +21,7 @@
 #include "k_morph.cuh"
 #include "k_prep.cuh"
 #include "k_rects.cuh"
+#include "host_ingest.cuh"
 
 static std::string g_create_error;
 

@@ -212,3 +212,55 @@ def test_fitsio_lite_lazy_header_and_column_reader(tmp_path):
         fitsio_lite.read_columns(q, ("ROWC", "NOSUCHCOLUMN"))
     with pytest.raises(ValueError):
         fitsio_lite.read_columns(p, ("ROWC",))      # an image HDU, not a table
+
+
+def test_native_ingest_equals_python(tmp_path):
+    """lfd_fits_load_frame / lfd_catalog_rects (host code of the C-ABI library, no GPU needed) against the Python
+    readers they stand in for: same payload bytes, same header values, same rectangles for every filter; files that
+    are not of the plain kind are declined (None) so that the driver falls back to the Python path."""
+    from lfd_b200 import detecttrails as dtm
+    kinds = {(flt, field): kind for field, kind in ((100, "sparse"), (101, "dense"), (102, "trail")) for flt in "ugriz"}
+    tree = synth.write_sdss_tree(str(tmp_path), 2888, 1, [100, 101, 102], filters=tuple("ugriz"), kinds=kinds)
+    lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], str(tmp_path))
+    H, W = synth.FRAME_H, synth.FRAME_W
+    slot_n, slot_p = np.zeros((H, W), np.uint32), np.zeros((H, W), np.uint32)
+    for field in (100, 101, 102):
+        for flt in "ugriz":
+            fpath = sdssfiles.filename("frame", run=2888, camcol=1, field=field, filter=flt)
+            raw = _lib.fits_load_frame(fpath, slot_n)
+            hdr = fitsio_lite.read_raw_image_into(fpath, slot_p)
+            assert raw is not None and np.array_equal(slot_n, slot_p)
+            for k in _lib.HEADER_KEYS:
+                assert fitsio_lite._parse_value(raw[k]) == hdr[k], k
+            assert dtm._results_prefix(2888, 1, flt, field, dtm._RawHeader(raw)) == dtm._results_prefix(2888, 1, flt, field, hdr)
+            opath = sdssfiles.filename("photoObj", run=2888, camcol=1, field=field)
+            got = _lib.catalog_rects(opath, flt, (H, W), **rp.DEFAULT_REMOVESTARS)
+            ref = star_rects(lfd_b200.removestars.read_photoObj_arrays(opath), flt, (H, W), **rp.DEFAULT_REMOVESTARS)
+            assert got is not None and got.dtype == np.int32 and np.array_equal(got, ref), (field, flt)
+    # other parameter values (fractional defaults, tight caps) and another frame shape go through the same arithmetic
+    opath = sdssfiles.filename("photoObj", run=2888, camcol=1, field=101)
+    cat = lfd_b200.removestars.read_photoObj_arrays(opath)
+    for pr in (dict(rp.DEFAULT_REMOVESTARS, defaultxy=20.7, maxxy=33.5, pixscale=0.25, magcount=1, maxmagdiff=1.5),
+               dict(rp.DEFAULT_REMOVESTARS, filter_caps={k: 19.5 for k in "ugriz"}, maxxy=1000)):
+        for shape in ((H, W), (700, 900)):
+            assert np.array_equal(_lib.catalog_rects(opath, "i", shape, **pr), star_rects(cat, "i", shape, **pr))
+    # declined: wrong slot shape, an image where a table is expected (and vice versa), a missing file, a NaN in the table
+    assert _lib.fits_load_frame(fpath, np.zeros((H, W + 4), np.uint32)) is None
+    assert _lib.fits_load_frame(opath, slot_n) is None
+    assert _lib.catalog_rects(fpath, "r", (H, W), **rp.DEFAULT_REMOVESTARS) is None
+    assert _lib.catalog_rects(str(tmp_path / "nosuch.fits"), "r", (H, W), **rp.DEFAULT_REMOVESTARS) is None
+    bad = {k: np.array(v, copy=True) for k, v in cat.items()}
+    bad["PETROTH90"] = bad["PETROTH90"].astype(np.float32); bad["PETROTH90"][5, 1] = np.inf
+    q = str(tmp_path / "bad.fits")
+    fitsio_lite.write_bintable(q, bad)
+    assert _lib.catalog_rects(q, "r", (H, W), **rp.DEFAULT_REMOVESTARS) is None
+    # the loader takes the native path by default and the Python path on request: same record either way
+    fr = (2888, 1, "g", 101)
+    a = dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_n, False)
+    old = dtm.NATIVE_INGEST
+    try:
+        dtm.NATIVE_INGEST = False
+        b = dtm._resolve_rects([dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_p, False)], [fr], (H, W), rp.DEFAULT_REMOVESTARS)[0]
+    finally:
+        dtm.NATIVE_INGEST = old
+    assert a[0] == b[0] == "staged" and np.array_equal(a[3], b[3]) and a[4] == b[4] and np.array_equal(slot_n, slot_p)
