@@ -270,7 +270,7 @@ def dropin_leg(device, ndistinct=32, nfields=256, batch=32):
         nlines = sum(1 for _ in open(os.path.join(out, "results.txt")))
         return {"value": nfields / best, "unit": "frames/s", "frames": nfields, "batch": batch, "detections": nlines,
                 "how": "DetectTrails(run, camcol, filter).process() on a synthetic tree in %s (%d distinct fields hard-linked to %d): "
-                       "raw FITS payload read into pinned staging by loader threads (page cache), photoObj filtering, ring of three "
+                       "raw FITS payload read into pinned staging and photoObj filtering by loader threads through the library's host-side ingest (page cache), ring of three "
                        "handles, results.txt written; best of 2 after a warm-up pass" % (tempfile.gettempdir(), ndistinct, nfields)}
     finally:
         shutil.rmtree(root, ignore_errors=True)
