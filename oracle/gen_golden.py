@@ -6,6 +6,8 @@
   :459-496 write 1equBRIGHT/2dilateBRIGHT/3contoursBRIGHT/6equDIM/7erodedDIM/8openedDIM/9contoursDIM PNGs,
   read back losslessly), the (bool, dict) returns of process_field_bright/dim and the clipped float image.
 * golden_full.npz : 2048x1489 frames; returns of both passes + SHA-1 of every debug tap.
+* golden_params.npz : the small frames with non-default parameter sets (BASELINE.json config 4: larger dilation
+  kernel, finer rho; other thresholds / clip values): returns + SHA-1 of every debug tap.
 * golden_run.npz  : a synthetic SDSS tree run through the reference's DetectTrails(...).process() with the
   fitsio stand-in: the bytes of results.txt / errors.txt and the frame visiting order for every _pick mode.
 
@@ -41,13 +43,22 @@ def small_frame(seed, nstars, peak):
     return img
 
 
-def run_with_taps(pf, img, dbg):
+# non-default parameter sets (BASELINE.json config 4: larger dilation, finer rho; other thresholds / clip values)
+def param_sets():
+    ones = lambda a, b: np.ones((a, b), np.uint8)   # noqa: E731
+    return [("config4_dilate", {"dilateKernel": ones(9, 9)}, {"dilateKernel": ones(15, 15)}),
+            ("config4_rho", {"houghMethod": 5}, {"dilateKernel": ones(15, 15), "houghMethod": 2}),
+            ("thresholds", {"dilateKernel": ones(3, 3), "nlinesInSet": 5, "lwTresh": 3},
+             {"erodeKernel": ones(3, 3), "dilateKernel": ones(9, 9), "minFlux": 0.03, "addFlux": 1.5})]
+
+
+def run_with_taps(pf, img, dbg, over_bright=None, over_dim=None):
     """Both passes of the reference with debug=True; returns dict of outputs."""
     os.environ["DEBUG_PATH"] = dbg
     pf.setup_debug()
     from oracle import ref_pipeline as rp
-    pb = dict(rp.DEFAULT_BRIGHT, debug=True)
-    pd = dict(rp.DEFAULT_DIM, debug=True)
+    pb = dict(rp.DEFAULT_BRIGHT, debug=True, **(over_bright or {}))
+    pd = dict(rp.DEFAULT_DIM, debug=True, **(over_dim or {}))
     out = {}
     work = np.ascontiguousarray(img[::-1]).copy()
     stdout = sys.stdout
@@ -92,6 +103,18 @@ def main():
                 else:
                     full["%s_%d_%s_sha1" % (kind, seed, k)] = np.frombuffer(hashlib.sha1(np.ascontiguousarray(v).tobytes()).digest(), np.uint8)
         np.savez_compressed(os.path.join(GOLD, "golden_full.npz"), cv2_version=cv2.__version__, **full)
+        # non-default parameters on the small frames: returns + SHA-1 of every tap
+        par = {}
+        for name, ob, od in param_sets():
+            for tag, seed, nstars, peak in SMALL_CASES:
+                out = run_with_taps(pf, small_frame(seed, nstars, peak), dbg, ob, od)
+                for k, v in out.items():
+                    key = "%s_%s_%s" % (name, tag, k)
+                    if k.startswith("ret_"):
+                        par[key] = v
+                    else:
+                        par[key + "_sha1"] = np.frombuffer(hashlib.sha1(np.ascontiguousarray(v).tobytes()).digest(), np.uint8)
+        np.savez_compressed(os.path.join(GOLD, "golden_params.npz"), cv2_version=cv2.__version__, **par)
 
     # whole-driver run through the reference's DetectTrails
     dtmod = lr.load_detecttrails()

@@ -97,3 +97,37 @@ def test_results_txt_golden(tmp_path):
     assert got_err.splitlines()[0] == ref_err.splitlines()[0] == "2888 1 r 555"
     assert got_err.splitlines()[-2] == ref_err.splitlines()[-2]
     assert "FileNotFoundError" in got_err
+
+
+def _param_sets():
+    ones = lambda a, b: np.ones((a, b), np.uint8)   # noqa: E731  (same sets as oracle/gen_golden.py::param_sets)
+    return [("config4_dilate", {"dilateKernel": ones(9, 9)}, {"dilateKernel": ones(15, 15)}),
+            ("config4_rho", {"houghMethod": 5}, {"dilateKernel": ones(15, 15), "houghMethod": 2}),
+            ("thresholds", {"dilateKernel": ones(3, 3), "nlinesInSet": 5, "lwTresh": 3},
+             {"erodeKernel": ones(3, 3), "dilateKernel": ones(9, 9), "minFlux": 0.03, "addFlux": 1.5})]
+
+
+@pytest.mark.parametrize("pi", range(3))
+def test_nondefault_params_goldens(pi):
+    """Non-default parameter sets (BASELINE.json config 4: larger dilation kernel, finer rho; other thresholds and
+    clip values) against the unmodified reference: returns and SHA-1 of every debug tap on the small frames."""
+    from lfd_b200 import _lib
+    g = np.load(os.path.join(GOLD, "golden_params.npz"))
+    name, ob, od = _param_sets()[pi]
+    h = _lib.Handle(300, 420, max_batch=1)
+    try:
+        h.set_params(dict(rp.DEFAULT_BRIGHT, **ob), dict(rp.DEFAULT_DIM, **od))
+        for tag in "abc":
+            gs = np.load(os.path.join(GOLD, "golden_small_%s.npz" % tag))
+            peak = float(gs["peak"])
+            trails = [] if peak == 0 else [{"p0": (10, 20), "p1": (400, 270), "sigma": 2.5, "peak": peak}]
+            img, _ = synth.make_frame(int(gs["seed"]), n_stars=int(gs["nstars"]), h=300, w=420, trails=trails)
+            out = _run_both(h, np.ascontiguousarray(img[::-1]))
+            for k, v in out.items():
+                key = "%s_%s_%s" % (name, tag, k)
+                if k.startswith("ret_"):
+                    assert v == g[key].tolist(), key
+                else:
+                    assert np.array_equal(sha(v), g[key + "_sha1"]), key
+    finally:
+        h.close()

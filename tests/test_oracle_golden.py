@@ -83,3 +83,33 @@ def test_results_txt_of_reference_run(cv2mod, tmp_path):
             if det:
                 out += rp.result_line(2888, 1, flt, field, hdr, res)
     assert out == str(g["results_txt"])
+
+
+def _param_sets():
+    ones = lambda a, b: np.ones((a, b), np.uint8)   # noqa: E731  (same sets as oracle/gen_golden.py::param_sets)
+    return [("config4_dilate", {"dilateKernel": ones(9, 9)}, {"dilateKernel": ones(15, 15)}),
+            ("config4_rho", {"houghMethod": 5}, {"dilateKernel": ones(15, 15), "houghMethod": 2}),
+            ("thresholds", {"dilateKernel": ones(3, 3), "nlinesInSet": 5, "lwTresh": 3},
+             {"erodeKernel": ones(3, 3), "dilateKernel": ones(9, 9), "minFlux": 0.03, "addFlux": 1.5})]
+
+
+@pytest.mark.parametrize("pi", range(3))
+def test_nondefault_params_against_reference(cv2mod, pi):
+    """Non-default parameter sets (BASELINE.json config 4 among them): the oracle reproduces the unmodified
+    reference's returns and every debug tap (SHA-1) on the small frames."""
+    g = np.load(os.path.join(GOLD, "golden_params.npz"))
+    assert str(g["cv2_version"]) == cv2mod.__version__, "goldens were generated with another cv2"
+    name, ob, od = _param_sets()[pi]
+    for tag in "abc":
+        work = np.ascontiguousarray(small_frame(np.load(os.path.join(GOLD, "golden_small_%s.npz" % tag)))[::-1])
+        tb, td = {}, {}
+        rb = rp.bright_pass(work, taps=tb, **dict(rp.DEFAULT_BRIGHT, **ob))
+        pre = "%s_%s_" % (name, tag)
+        assert np.array_equal(sha(work), g[pre + "clipped_bright_sha1"])
+        rd = rp.dim_pass(work, taps=td, **dict(rp.DEFAULT_DIM, **od))
+        assert np.array_equal(sha(work), g[pre + "clipped_dim_sha1"])
+        assert enc(rb) == g[pre + "ret_bright"].tolist() and enc(rd) == g[pre + "ret_dim"].tolist(), (name, tag)
+        for key, arr in (("1equBRIGHT", tb["equ"]), ("2dilateBRIGHT", tb["morph"]), ("3contoursBRIGHT", tb["box_img"]),
+                         ("6equDIM", td["equ"]), ("7erodedDIM", td["eroded"]), ("8openedDIM", td["morph"]),
+                         ("9contoursDIM", td["box_img"])):
+            assert np.array_equal(sha(arr), g[pre + key + "_sha1"]), (name, tag, key)
