@@ -26,7 +26,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/stat.h>
 #include <unistd.h>
 
 #include <string>
@@ -122,8 +121,6 @@ static long data_bytes(const std::vector<Card>& cards)
     card_int(cards, "GCOUNT", &gcount); card_int(cards, "PCOUNT", &pcount);
     return labs(bitpix) / 8 * gcount * (pcount + n);
 }
-
-static inline long pad_block(long n) { return (n + FITS_BLOCK - 1) / FITS_BLOCK * FITS_BLOCK; }
 
 static inline float be_f32(const unsigned char* p)
 {
