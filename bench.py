@@ -240,7 +240,7 @@ def bind_to_gpu_numa_node(gpu):
     return None
 
 
-def dropin_leg(device, ndistinct=32, nfields=256, batch=32):
+def dropin_leg(device, ndistinct=32, nfields=1024, batch=32):
     """Frames/s of the user-facing call: a synthetic SDSS tree on local disk (FITS frames + photoObj tables),
     lfd_b200.DetectTrails(run=, camcol=, filter=).process() writing results.txt - FITS reads (page cache), catalog
     filtering, pinned staging, H2D, kernels, D2H and the text output all inside the timed region.  `ndistinct`

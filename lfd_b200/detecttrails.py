@@ -436,7 +436,9 @@ def process_fields(results, errors, frames, params_bright, params_dim, params_re
         done = read_progress(progress)
         frames = [fr for fr in frames if _progress_key(fr) not in done]
     writer = (not distributed) or sharding.rank() == 0
-    chunk = max(batch, 1) * (sharding.world_size() if distributed else 1) * 8
+    # frames per compute call: the ring drains and refills at every call boundary (one un-overlapped batch load plus
+    # one un-overlapped batch of compute, ~15 ms), so calls are long; a progress file is extended once per call
+    chunk = max(batch, 1) * (sharding.world_size() if distributed else 1) * 32
     for i0 in range(0, len(frames), chunk):
         part = frames[i0:i0 + chunk]
         recs = sharding.run_sharded(part, compute, block=batch) if distributed else compute(part)
