@@ -240,7 +240,7 @@ def bind_to_gpu_numa_node(gpu):
     return None
 
 
-def dropin_leg(device, ndistinct=32, nfields=1024, batch=32):
+def dropin_leg(device, ndistinct=32, nfields=1024, batch=32, verify=True):
     """Frames/s of the user-facing call: a synthetic SDSS tree on local disk (FITS frames + photoObj tables),
     lfd_b200.DetectTrails(run=, camcol=, filter=).process() writing results.txt - FITS reads (page cache), catalog
     filtering, pinned staging, H2D, kernels, D2H and the text output all inside the timed region.  `ndistinct`
@@ -267,8 +267,23 @@ def dropin_leg(device, ndistinct=32, nfields=1024, batch=32):
             el = time.perf_counter() - t0
             if rep_i > 0:
                 best = el if best is None else min(best, el)
-        nlines = sum(1 for _ in open(os.path.join(out, "results.txt")))
+        got = open(os.path.join(out, "results.txt")).read()
+        nlines = got.count("\n")
+        verified = None
+        if verify:
+            # checker: the oracle's lines for the distinct fields, repeated for the hard-linked names
+            from oracle import ref_pipeline as rp
+            from oracle.verdicts import verdicts
+            from lfd_b200 import fitsio_lite
+            src_fields = list(range(100, 100 + ndistinct))
+            ref = verdicts([tree["frames"][("r", f)][0] for f in src_fields], [tree["frames"][("r", f)][1] for f in src_fields],
+                           ["r"] * ndistinct)
+            hdrs = [fitsio_lite.read_header(os.path.join(fdir, "frame-r-002888-1-%04d.fits" % f)) for f in src_fields]
+            exp = "".join(rp.result_line(2888, 1, "r", 100 + k, hdrs[k % ndistinct], ref[k % ndistinct][2])
+                          for k in range(nfields) if ref[k % ndistinct][0] is True)
+            verified = nfields if got == exp else 0
         return {"value": nfields / best, "unit": "frames/s", "frames": nfields, "batch": batch, "detections": nlines,
+                "verified": verified,
                 "how": "DetectTrails(run, camcol, filter).process() on a synthetic tree in %s (%d distinct fields hard-linked to %d): "
                        "raw FITS payload read into pinned staging and photoObj filtering by loader threads through the library's host-side ingest (page cache), ring of three "
                        "handles, results.txt written; best of 2 after a warm-up pass" % (tempfile.gettempdir(), ndistinct, nfields)}
@@ -333,9 +348,11 @@ def run_ours(args):
     t0 = time.perf_counter()
     prep_ms_sum = 0.0
     hA.timer_mark(0)
+    res_resident = None
     for _ in range(args.steps):
-        hA.run_resident(B); hA.wait()
+        hA.run_resident(B); res_resident = hA.wait()
         prep_ms_sum += hA.timings()[1][1]             # k_prep runs before the passes fork: its bracket is clean
+    res_resident = [bytes(r) for r in res_resident]
     hA.timer_mark(1)
     dev_ms = hA.timer_elapsed_ms(0, hA, 1)            # CUDA events on the library's stream, first launch -> last result
     torch.cuda.synchronize()
@@ -373,14 +390,14 @@ def run_ours(args):
         for k in range(1, steps):
             hs[k & 1].submit(B, rects)
             hs[(k - 1) & 1].wait()
-        hs[(steps - 1) & 1].wait()
+        return hs[(steps - 1) & 1].wait()
     e2e_loop(max(args.warmup, 2))
     barrier()
     l1 = hA.kernel_launches() + hB.kernel_launches()
     sampler.resume()
     t0 = time.perf_counter()
     hA.timer_mark(2)
-    e2e_loop(args.steps)
+    res_e2e = [bytes(r) for r in e2e_loop(args.steps)]
     last = (hA, hB)[(args.steps - 1) & 1]
     last.timer_mark(3)
     e2e_dev_ms = hA.timer_elapsed_ms(2, last, 3)      # device clock: first H2D enqueued -> last result copied back
@@ -405,6 +422,24 @@ def run_ours(args):
 
     launches_total = int(reduce_sum(launches + launches_e2e))
     os.sched_setaffinity(0, orig_affinity)     # the CPU baseline and the drop-in leg use every host core
+
+    # ---- verify: the results of the LAST TIMED step of both legs against the oracle, outside the timed regions ----
+    verified = mismatches = None
+    if not args.no_verify:
+        from oracle.verdicts import device_verdict, verdicts
+        filters = [synth.FILTERS[i % 5] for i in range(B)]
+        ref = verdicts(frames, cats, filters, cores=max((os.cpu_count() or 1) // world, 1))
+        ok = 0
+        for i in range(B):
+            want = tuple(ref[i])
+            got_r = device_verdict(_lib.Result.from_buffer_copy(res_resident[i]), (H, W))
+            got_e = device_verdict(_lib.Result.from_buffer_copy(res_e2e[i]), (H, W))
+            if got_r == want and got_e == want:
+                ok += 1
+            else:
+                print("verify: rank %d frame %d (%s): resident %s, e2e %s, oracle %s" % (rank, i, kinds[i], got_r, got_e, want), file=sys.stderr)
+        verified = int(reduce_sum(ok))
+        mismatches = int(reduce_sum(B - ok))
 
     if rank != 0:
         if distributed:
@@ -478,7 +513,7 @@ def run_ours(args):
     dropin = None
     if world == 1 and not args.no_dropin:
         try:
-            dropin = dropin_leg(local)
+            dropin = dropin_leg(local, verify=not args.no_verify)
         except Exception as e:   # noqa: BLE001 - an extra, never fatal for the contract line
             dropin = {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -497,6 +532,9 @@ def run_ours(args):
                 "ms_per_step": 1e3 * e2e_elapsed / args.steps, "h2d_only_ms_per_step": 1e3 * h2d_s,
                 "h2d_gbs": h2d_bytes / h2d_s / 1e9, "how": "lfd_submit from pinned host staging + lfd_wait, two handles double-buffered"},
         "gpu_launches": launches_total,
+        "verified": verified, "verify_mismatches": mismatches,
+        "verify_note": "verdict (detected, pass, end points) of every frame of the last timed step of the resident leg and of the "
+                       "e2e leg == oracle/ref_pipeline.py::process_frame on the same frame (all ranks; checker only, untimed)",
         "roofline": roofline,
         "stages": stage_report,
         "stages_note": "per-stage CUDA-event times of %d extra steps with the passes serialised (LFD_SERIAL_PASSES), %.3f ms/step; "
@@ -527,6 +565,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (target command for ncu)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the DetectTrails-on-FITS-files leg")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed steps' results")
+    ap.add_argument("--verify", action="store_true", help="(default) check the timed steps' results against the oracle")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

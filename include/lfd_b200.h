@@ -138,8 +138,8 @@ typedef struct lfd_rect {
 
 /* optional capacities for lfd_create_ex (0 = default) */
 typedef struct lfd_config {
-    int32_t max_runs;           /* runs per frame and mask kind (default 1<<20) */
-    int32_t max_components;     /* contours per frame and kind (default 1<<18) */
+    int32_t max_runs;           /* runs per frame, pass and mask kind (default 1<<19, at most height * ceil(width/2)) */
+    int32_t max_components;     /* contours per frame, pass and kind (default 1<<16) */
     int32_t max_star_rects;     /* blot squares per frame (default 8192) */
     int32_t max_lines;          /* HoughLines entries kept per frame in LFD_FULL_LINES mode (default numangle*numrho) */
     int32_t reserved[4];

@@ -106,6 +106,25 @@ static bool card_str(const std::vector<Card>& cards, const char* key, std::strin
     return true;
 }
 
+// numeric card value as a double ("1.0", "0.000000E+00", "1"); false if missing or not a number
+static bool card_num(const std::vector<Card>& cards, const char* key, double* out)
+{
+    const Card* c = find(cards, key);
+    if (!c) return false;
+    const char* p = c->value;
+    while (*p == ' ') p++;
+    char buf[72];
+    size_t n = 0;
+    while (p[n] && p[n] != ' ' && p[n] != '/' && n + 1 < sizeof buf) { buf[n] = (p[n] == 'D' || p[n] == 'd') ? 'E' : p[n]; n++; }
+    buf[n] = 0;
+    char* end = nullptr;
+    errno = 0;
+    double v = strtod(buf, &end);
+    if (end == buf || *end != 0 || errno) return false;
+    *out = v;
+    return true;
+}
+
 static long data_bytes(const std::vector<Card>& cards)
 {
     long naxis = 0, bitpix = 0;
@@ -161,7 +180,17 @@ extern "C" int lfd_fits_load_frame(const char* path, void* dest, int height, int
         long bitpix = 0, naxis = 0, n1 = 0, n2 = 0;
         if (!card_int(cards, "BITPIX", &bitpix) || !card_int(cards, "NAXIS", &naxis) || bitpix != -32 || naxis != 2) return LFD_E_UNSUPPORTED;
         if (!card_int(cards, "NAXIS1", &n1) || !card_int(cards, "NAXIS2", &n2) || n1 != width || n2 != height) return LFD_E_UNSUPPORTED;
-        if (find(cards, "BSCALE") || find(cards, "BZERO")) return LFD_E_UNSUPPORTED;     // scaled images: the Python reader applies them
+        // scaled images (BSCALE != 1 or BZERO != 0): the Python reader applies the scaling; the trivial cards many
+        // writers emit (BSCALE = 1, BZERO = 0) are plain payload
+        {
+            double bs = 1.0, bz = 0.0;
+            if (find(cards, "BSCALE") && !card_num(cards, "BSCALE", &bs)) return LFD_E_UNSUPPORTED;
+            if (find(cards, "BZERO") && !card_num(cards, "BZERO", &bz)) return LFD_E_UNSUPPORTED;
+            if (bs != 1.0 || bz != 0.0) return LFD_E_UNSUPPORTED;
+        }
+        // the caller's slot holds exactly height * width 4-byte pixels: a header that claims more (PCOUNT / GCOUNT) is not
+        // the plain layout
+        if (nbytes != (long)height * (long)width * 4) return LFD_E_UNSUPPORTED;
         for (int k = 0; k < nkeys; k++) {
             const Card* c = find(cards, keys[k]);
             if (!c) return LFD_E_UNSUPPORTED;            // the Python path raises the KeyError the reference would

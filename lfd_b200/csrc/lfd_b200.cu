@@ -25,6 +25,11 @@
 
 static std::string g_create_error;
 
+// dynamic shared-memory opt-in (cudaFuncSetAttribute) is per function AND per device: high-water marks per device
+#define LFD_MAX_DEVICES 64
+struct DevLimits { size_t band_max = 48 * 1024, rects_max = 48 * 1024, anyk_max = 48 * 1024; };
+static DevLimits g_dev_limits[LFD_MAX_DEVICES];
+
 enum { T_PREP = 0, T_MORPH, T_CANNY, T_CCL_FG, T_CCL_BG, T_RECTS, T_HOUGH, T_CHECK, T_PER_PASS };
 static const char* k_timing_names[] = {
     "setup(memset+star_mask)",
@@ -49,7 +54,7 @@ struct HoughBufs {
 };
 
 struct lfd_handle {
-    int device = 0, B = 0;
+    int device = 0, B = 0, sm_count = 148;
     Dims d;
     lfd_config cfg;
     lfd_params params;
@@ -386,6 +391,7 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
+        h->sm_count = prop.multiProcessorCount;
         int per_sm[3] = {0, 0, 0};
         // k_prep keeps its TMA rings in dynamic shared memory (above the 48 KB default limit)
 #define PREP_ATTR(M, E) CK(cudaFuncSetAttribute(k_prep<M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM))
@@ -396,16 +402,17 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_prep<2, false>, PR_WARPS * 32, PR_SMEM));
         for (int m = 0; m < 3; m++) h->prep_grid[m] = prop.multiProcessorCount * (per_sm[m] > 0 ? per_sm[m] : 1);
     }
-    // the dynamic shared-memory limit is a property of the FUNCTION, shared by every handle of the process: only ever raise it
+    // the dynamic shared-memory limit is a property of the FUNCTION on one DEVICE, shared by every handle of the process
+    // on that device: only ever raise it, and keep the high-water mark per device
     {
-        static size_t band_max = 48 * 1024, rects_max = 48 * 1024;
-        if (ccl_band_smem(h->d.WW) > band_max) {
-            band_max = ccl_band_smem(h->d.WW);
-            CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_max));
+        DevLimits& L = g_dev_limits[device % LFD_MAX_DEVICES];
+        if (ccl_band_smem(h->d.WW) > L.band_max) {
+            CK(cudaFuncSetAttribute(k_ccl_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ccl_band_smem(h->d.WW)));
+            L.band_max = ccl_band_smem(h->d.WW);
         }
-        if (rects_smem(max_batch) > rects_max) {
-            rects_max = rects_smem(max_batch);
-            CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_max));
+        if (rects_smem(max_batch) > L.rects_max) {
+            CK(cudaFuncSetAttribute(k_rects_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rects_smem(max_batch)));
+            L.rects_max = rects_smem(max_batch);
         }
     }
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
@@ -602,9 +609,9 @@ extern "C" int lfd_set_kernels(lfd_handle* h, int pass, const uint8_t* erode_mas
     CK(cudaMemcpy(h->anyk_d + pass * 2, &h->anyk_h[pass][0], 2 * sizeof(AnyKernel), cudaMemcpyHostToDevice));
     h->anyk_on[pass] = true;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-    static size_t anyk_max = 48 * 1024;
     size_t need = anyk_smem(h->anyk_h[pass][0].reach, h->anyk_h[pass][1].reach);
-    if (need > anyk_max) { anyk_max = need; CK(cudaFuncSetAttribute(k_morph_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)anyk_max)); }
+    DevLimits& L = g_dev_limits[h->device % LFD_MAX_DEVICES];
+    if (need > L.anyk_max) { CK(cudaFuncSetAttribute(k_morph_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)); L.anyk_max = need; }
     return LFD_OK;
 }
 
@@ -723,7 +730,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     k_ccl_extremes_flat<<<flat, 256, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 4);
     // rectangles + box image
-    k_rects_warp<<<148 * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d, v_edges, pp.contoursMode == 0 ? 1 : 0); LAUNCH_CHECK();
+    k_rects_warp<<<h->sm_count * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d, v_edges, pp.contoursMode == 0 ? 1 : 0); LAUNCH_CHECK();
     CK(cudaMemsetAsync(v_box, 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(v_rbuf, v_box, C, pass, d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 5);

@@ -303,6 +303,13 @@ def read_header(path, ext=0):
     raise OSError("extension %d not found in %s" % (ext, path))
 
 
+def _require_unscaled(h):
+    """The raw payload is only the image when no scaling applies: ``read`` multiplies by BSCALE and adds BZERO, the
+    raw upload path cannot, so anything but the trivial 1 / 0 takes the decoded path (ValueError -> caller falls back)."""
+    if h.get("BSCALE", 1) != 1 or h.get("BZERO", 0) != 0:
+        raise ValueError("raw upload path needs an unscaled image (BSCALE=1, BZERO=0)")
+
+
 def read_raw_image(path):
     """Return ``(payload_bytes_view, header)`` for the primary float32 image without byte-swapping.
 
@@ -314,6 +321,8 @@ def read_raw_image(path):
             continue
         if h["BITPIX"] != -32 or h["NAXIS"] != 2:
             raise ValueError("raw upload path needs a 2-D BITPIX=-32 image")
+        _require_unscaled(h)
+        nbytes = min(nbytes, 4 * h["NAXIS1"] * h["NAXIS2"])
         with open(path, "rb") as f:
             f.seek(pos)
             buf = f.read(nbytes)
@@ -332,6 +341,8 @@ def read_raw_image_into(path, dest):
                 continue
             if h["BITPIX"] != -32 or h["NAXIS"] != 2:
                 raise ValueError("raw upload path needs a 2-D BITPIX=-32 image")
+            _require_unscaled(h)
+            nbytes = min(nbytes, 4 * h["NAXIS1"] * h["NAXIS2"])
             if (h["NAXIS2"], h["NAXIS1"]) != tuple(dest.shape) or dest.dtype.itemsize != 4:
                 raise ValueError("image shape %s does not match the staging slot %s" % ((h["NAXIS2"], h["NAXIS1"]), dest.shape))
             f.seek(pos)

@@ -125,7 +125,21 @@ def make_catalog(seed, stars, extra_fake=10):
     }
 
 
-_KINDS = ("sparse", "trail", "dense", "satellite", "dense_trail", "faint_trail", "empty")
+_KINDS = ("sparse", "trail", "dense", "satellite", "dense_trail", "faint_trail", "empty", "trail_var", "trail_axis",
+          "dense_heavy")
+
+
+def _random_trail(rng, angle=None):
+    """One trail of SURVEY.md 8(d) config 3: any angle, width 2-15 px (FWHM of the Gaussian cross section), peak
+    0.3-50 (log-uniform), a random chord of the frame at least 600 px long."""
+    ang = rng.uniform(0, np.pi) if angle is None else angle
+    width = rng.uniform(2.0, 15.0)
+    peak = float(np.exp(rng.uniform(np.log(0.3), np.log(50.0))))
+    cx, cy = rng.uniform(0.25 * FRAME_W, 0.75 * FRAME_W), rng.uniform(0.25 * FRAME_H, 0.75 * FRAME_H)
+    L = rng.uniform(600.0, 2600.0)
+    return {"p0": (cx - L / 2 * np.cos(ang), cy - L / 2 * np.sin(ang)),
+            "p1": (cx + L / 2 * np.cos(ang), cy + L / 2 * np.sin(ang)),
+            "sigma": float(width / 2.3548), "peak": peak}
 
 
 def make_case(kind, seed):
@@ -155,23 +169,40 @@ def make_case(kind, seed):
             {"p0": (0, 300 + off), "p1": (2047, 900 + off), "sigma": 2.5, "peak": 5.0}])
     elif kind == "empty":
         img, st = make_frame(seed, n_stars=0)
+    elif kind == "trail_var":
+        img, st = make_frame(seed, n_stars=int(rng.integers(100, 500)), trails=[_random_trail(rng)])
+    elif kind == "trail_axis":
+        # near-horizontal / near-vertical trails: 0 or 90 degrees +- 1 degree
+        base = (0.0, np.pi / 2)[int(rng.integers(0, 2))]
+        img, st = make_frame(seed, n_stars=int(rng.integers(100, 500)),
+                             trails=[_random_trail(rng, base + np.deg2rad(rng.uniform(-1.0, 1.0)))])
+    elif kind == "dense_heavy":
+        img, st = make_frame(seed, n_stars=int(rng.integers(6000, 10001)))
     else:
         raise ValueError("unknown case kind %r (known: %s)" % (kind, ", ".join(_KINDS)))
     return img, make_catalog(seed, st)
 
 
 def case_for_frame(run, camcol, filter, field):
-    """Config-3 style mix: ~5 % trails, ~2 % satellites, ~10 % dense, rest sparse."""
+    """Config-3 mix: ~7 % trails (any angle incl. near-horizontal / near-vertical, width 2-15 px, peak
+    0.3-50, plus faint ones), ~2 % satellites (two parallel trails), ~10 % dense fields (3 000-10 000 stars), rest
+    sparse (100-500 stars)."""
     seed = frame_seed(run, camcol, filter, field)
     u = np.random.default_rng(seed ^ 0x77).random()
-    if u < 0.03:
+    if u < 0.01:
         kind = "trail"
-    elif u < 0.05:
-        kind = "faint_trail"
+    elif u < 0.04:
+        kind = "trail_var"
+    elif u < 0.055:
+        kind = "trail_axis"
     elif u < 0.07:
+        kind = "faint_trail"
+    elif u < 0.09:
         kind = "satellite"
-    elif u < 0.17:
+    elif u < 0.14:
         kind = "dense"
+    elif u < 0.19:
+        kind = "dense_heavy"
     else:
         kind = "sparse"
     return kind, seed

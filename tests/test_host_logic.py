@@ -264,3 +264,35 @@ def test_native_ingest_equals_python(tmp_path):
     finally:
         dtm.NATIVE_INGEST = old
     assert a[0] == b[0] == "staged" and np.array_equal(a[3], b[3]) and a[4] == b[4] and np.array_equal(slot_n, slot_p)
+
+
+def test_scaled_frames_take_the_decoded_path(tmp_path):
+    """A frame header with the trivial BSCALE = 1 / BZERO = 0 cards is plain payload for both raw readers (the native
+    ingest must not decline it); a non-trivial scaling makes both decline, so that the driver decodes on the host like
+    fitsio.read does (detecttrails.py:113)."""
+    from lfd_b200 import _lib, fitsio_lite
+    H, W = 40, 64
+    img = np.random.default_rng(3).normal(0, 1, (H, W)).astype(np.float32)
+    hdr = dict(synth.DEFAULT_HEADER)
+    triv = str(tmp_path / "triv.fits")
+    fitsio_lite.write_image(triv, img, dict(hdr, BSCALE=1.0, BZERO=0.0))
+    scaled = str(tmp_path / "scaled.fits")
+    fitsio_lite.write_image(scaled, img, dict(hdr, BSCALE=2.0, BZERO=0.5))
+    want = img.astype(">f4").view(np.uint32)
+    slot = np.zeros((H, W), np.uint32)
+    raw = _lib.fits_load_frame(triv, slot)
+    assert raw is not None and np.array_equal(slot, want)
+    slot2 = np.zeros((H, W), np.uint32)
+    fitsio_lite.read_raw_image_into(triv, slot2)
+    assert np.array_equal(slot2, want) and np.array_equal(fitsio_lite.read_raw_image(triv)[0], want)
+    assert _lib.fits_load_frame(scaled, slot) is None
+    with pytest.raises(ValueError):
+        fitsio_lite.read_raw_image(scaled)
+    with pytest.raises(ValueError):
+        fitsio_lite.read_raw_image_into(scaled, slot2)
+    assert np.allclose(fitsio_lite.read(scaled), img * 2.0 + 0.5)
+    # a header that claims more data than the image (PCOUNT) must not overrun the caller's slot
+    big = str(tmp_path / "pcount.fits")
+    fitsio_lite.write_image(big, img, dict(hdr, PCOUNT=4096, GCOUNT=1))
+    guard = np.zeros((H + 8, W), np.uint32)
+    assert _lib.fits_load_frame(big, guard[:H]) is None and not guard[H:].any()
