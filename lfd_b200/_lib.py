@@ -9,7 +9,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "liblfd_b200.so")
+LIB_PATH = os.environ.get("LFD_B200_LIB") or os.path.join(HERE, "liblfd_b200.so")     # env override: A/B builds in profiles/lab
 SRC = os.path.join(HERE, "csrc", "lfd_b200.cu")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",

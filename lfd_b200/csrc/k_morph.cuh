@@ -294,23 +294,31 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 
     // software pipeline: the U rows of the next block are requested before the current block is processed,
     // so the dependent min/max chain never waits on a global load (the kernel is latency-, not bandwidth-bound)
-    // Pixels outside the frame are "ignored" by cv2: they enter as the identity of the FIRST filter (255 for the
-    // erosion, 0 for the dilation) already at load time, so the row body has no special cases.  Row addresses are
-    // running element offsets (one 64-bit add per row instead of a 64-bit multiply chain per access).
-    const u32 identw = HAS_E ? 0xffffffffu : 0u;
+    // Pixels outside the frame are "ignored" by cv2: they are loaded as zeros (so that the all-zero test below sees
+    // only frame pixels) and become the identity of the FIRST filter (255 for the erosion, 0 for the dilation) where a
+    // row is actually filtered.  Row addresses are running element offsets (one 64-bit add per row instead of a
+    // 64-bit multiply chain per access).
+    //
+    // All-zero rows are the common case on sky-subtracted frames (bright: everything but stars; dim: everything the
+    // erosion removes): one warp vote per row skips the horizontal window, and the vertical reduction + LUT + mask
+    // bits are skipped while every row of the dilation ring is zero (ezbits / dnz track the rings' all-zero rows).
     const long long rstep = Ww >> 1;                           // uint2 elements per image row
     long long ld_off = ((long long)yfirst * Ww + wx) >> 1;     // arithmetic shift: also right for rows above the frame
     uint2 nxt[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int y = yfirst + u;
-        nxt[u] = make_uint2(identw, identw);
+        nxt[u] = make_uint2(0u, 0u);
         if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + ld_off);
         ld_off += rstep;
     }
     long long st_off = ((long long)y0 * Ww + wx) >> 1;          // output rows are produced in order y0, y0+1, ...
     long long et_off = st_off;
     int nz_off = f * d.NW + y0 * d.WW + mw;
+    u32 ezbits = (1u << EHR) - 1u;                             // erosion ring rows that are all-zero across the strip
+    u32 dnz = 0;                                               // dilation ring rows that are NOT all-zero
+    const bool lut0z = lut0 == 0u;
+    const bool nz_lane = (r & 3) == 0 && lane >= 2 && lane < 30 && mw < d.WW;
     for (int yb = yfirst; yb <= ylast; yb += U) {
         uint2 cur[U];
 #pragma unroll
@@ -319,7 +327,7 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int y = yb + U + u;
-                nxt[u] = make_uint2(identw, identw);
+                nxt[u] = make_uint2(0u, 0u);
                 if (y >= 0 && y < d.H && col_in) nxt[u] = __ldg(g + ld_off);
                 ld_off += rstep;
             }
@@ -327,21 +335,40 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int y = yb + u;
-            const uint2 v = cur[u];
-            u32 p[4];
-            p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
-            p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
+            uint2 v = cur[u];
+            const bool yin = (unsigned)y < (unsigned)d.H;
+            const bool in_zero = !__any_sync(FULLMASK, (v.x | v.y) != 0u);
             u32 e[4];
+            bool e_zero;                                     // warp-uniform: the row entering the dilation is all-zero
             int ye = y;
             if (HAS_E) {
-                u32 hm[4];
-                hwin16<false, E_L, E_R>(p, hm);
-#pragma unroll
-                for (int c = 0; c < 4; c++) eR[u % EHR][c] = hm[c];
                 ye = y - E_B;
-                const bool ein = col_in && ye >= 0 && ye < d.H;
+                if (in_zero && yin) {                        // a frame row of zeros: every minimum that sees it is zero
+                    if (!((ezbits >> (u % EHR)) & 1u)) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) e[c] = ein ? vreduce16<false, EHR>(eR, c) : 0u;
+                        for (int c = 0; c < 4; c++) eR[u % EHR][c] = 0;
+                        ezbits |= 1u << (u % EHR);
+                    }
+                } else {
+                    if (!(yin && col_in)) v = make_uint2(0xffffffffu, 0xffffffffu);
+                    u32 p[4], hm[4];
+                    p[0] = __byte_perm(v.x, 0, 0x4140); p[1] = __byte_perm(v.x, 0, 0x4342);
+                    p[2] = __byte_perm(v.y, 0, 0x4140); p[3] = __byte_perm(v.y, 0, 0x4342);
+                    hwin16<false, E_L, E_R>(p, hm);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) eR[u % EHR][c] = hm[c];
+                    ezbits &= ~(1u << (u % EHR));
+                }
+                if (ezbits != 0u) {                          // a zero row in the window: the minimum is zero
+#pragma unroll
+                    for (int c = 0; c < 4; c++) e[c] = 0u;
+                    e_zero = true;
+                } else {
+                    const bool ein = col_in && ye >= 0 && ye < d.H;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) e[c] = ein ? vreduce16<false, EHR>(eR, c) : 0u;
+                    e_zero = !__any_sync(FULLMASK, (e[0] | e[1] | e[2] | e[3]) != 0u);
+                }
                 if (et && ye >= y0 && ye < y1) {
                     u32 w0, w1;
                     lut_pack(e, slut, w0, w1);
@@ -349,31 +376,43 @@ k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __res
                     et_off += rstep;
                 }
             } else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) e[c] = p[c];
+                e_zero = in_zero;
             }
-            u32 hd[4];
-            hwin16<true, D_L, D_R>(e, hd);
+            if (e_zero) {
+                if ((dnz >> (u % DH)) & 1u) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) dR[u % DH][c] = hd[c];
+                    for (int c = 0; c < 4; c++) dR[u % DH][c] = 0;
+                    dnz &= ~(1u << (u % DH));
+                }
+            } else {
+                if (!HAS_E) {
+                    e[0] = __byte_perm(v.x, 0, 0x4140); e[1] = __byte_perm(v.x, 0, 0x4342);
+                    e[2] = __byte_perm(v.y, 0, 0x4140); e[3] = __byte_perm(v.y, 0, 0x4342);
+                }
+                u32 hd[4];
+                hwin16<true, D_L, D_R>(e, hd);
+#pragma unroll
+                for (int c = 0; c < 4; c++) dR[u % DH][c] = hd[c];
+                dnz |= 1u << (u % DH);
+            }
             const int yo = ye - D_B;
             if (yo >= y0 && yo < y1) {                       // warp-uniform
-                u32 o[4];
+                u32 w0 = 0, w1 = 0, bits = 0;
+                if (dnz != 0u || !lut0z) {                   // (an all-zero window gives lut[0] == 0 everywhere)
+                    u32 o[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) o[c] = vreduce16<true, DH>(dR, c);
-                u32 w0 = 0, w1 = 0;
-                const bool anynz = __any_sync(FULLMASK, (o[0] | o[1] | o[2] | o[3]) != 0u);
-                if (anynz || lut0 != 0u) lut_pack(o, slut, w0, w1);
-                if (!lane_out) { w0 = 0; w1 = 0; }
+                    for (int c = 0; c < 4; c++) o[c] = vreduce16<true, DH>(dR, c);
+                    lut_pack(o, slut, w0, w1);
+                    if (!lane_out) { w0 = 0; w1 = 0; }
+                    if (__any_sync(FULLMASK, (w0 | w1) != 0u)) {
+                        bits = (nzbits4(w0) | (nzbits4(w1) << 4)) << q8;
+                        bits |= __shfl_sync(FULLMASK, bits, src1);
+                        bits |= __shfl_sync(FULLMASK, bits, src2);
+                    }
+                }
                 if (lane_out) mo[st_off] = make_uint2(w0, w1);
                 st_off += rstep;
-                u32 bits = 0;
-                if (anynz || lut0 != 0u) {
-                    bits = (nzbits4(w0) | (nzbits4(w1) << 4)) << q8;
-                    bits |= __shfl_sync(FULLMASK, bits, src1);
-                    bits |= __shfl_sync(FULLMASK, bits, src2);
-                }
-                if ((r & 3) == 0 && lane >= 2 && lane < 30 && mw < d.WW) nz[nz_off] = bits;
+                if (nz_lane) nz[nz_off] = bits;
                 nz_off += d.WW;
             }
         }

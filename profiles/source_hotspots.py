@@ -28,5 +28,6 @@ for r in rows:
             pass
 tot = sum(v[1] for v in agg.values()); toti = sum(v[2] for v in agg.values())
 print("samples", tot, "instructions", toti)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
+by = 2 if (len(sys.argv) > 3 and sys.argv[3] == "ins") else 1
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][by])[:topn]:
     print("%5.1f%% smp %5.1f%% ins  %s:%s  %s" % (100 * v[1] / max(tot, 1), 100 * v[2] / max(toti, 1), k[0], k[1], v[0].strip()[:110]))

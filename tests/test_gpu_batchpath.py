@@ -93,6 +93,15 @@ def test_production_batches_match_oracle(cv2mod):
         res3 = h.wait()
         for j in range(n):
             assert device_verdict(res3[j], frames[0].shape) == tuple(ref[100 + j]), (j, kinds[100 + j])
+        # edge maps and box images the untapped (fused, graph) path left behind == the oracle's, pixel for pixel
+        picked = [j for j in range(n) if ref[100 + j][0] is True][:3] + [j for j in range(n) if ref[100 + j][0] is False][:2]
+        for j in picked:
+            taps = {}
+            rp.process_frame(frames[100 + j].copy(), cats[100 + j], filters[100 + j], taps=taps)
+            for p, key in ((0, "bright"), (1, "dim")):
+                if taps[key]:
+                    assert np.array_equal(h.stage(j, p, "canny"), taps[key]["canny"]), (j, key, "canny")
+                    assert np.array_equal(h.stage(j, p, "box"), taps[key]["box_img"]), (j, key, "box")
     finally:
         for h in hs:
             h.close()
