@@ -64,6 +64,8 @@ extern "C" {
 #define LFD_KEEP_TAPS 2         /* materialise the uint8 stage images for lfd_get_stage */
 #define LFD_FULL_LINES 4        /* sort and keep the full HoughLines lists (taps / parity) */
 #define LFD_SERIAL_PASSES 8     /* run the dim pass after the bright pass on one stream (per-stage timings) */
+#define LFD_KERNEL_TIMES 16     /* bracket the kernels that carry the step with CUDA events (lfd_get_kernel_times); the ~50
+                                   extra event nodes cost about 5 % of a 64-frame step, so this is off by default */
 
 /* stage ids for lfd_get_stage (uint8 H*W unless noted) */
 enum lfd_stage {
@@ -213,6 +215,12 @@ int lfd_fit_min_area_rect(lfd_handle* h, const uint8_t* img, int contoursMode, i
 
 /* Per-stage device times (ms, CUDA events) of the last lfd_wait / lfd_run_resident; names via lfd_stage_name. */
 int lfd_get_timings(lfd_handle* h, float* ms, int max_entries, int* n_entries);
+/* Bracketed kernels (the ones that carry the step: morphology, Sobel/NMS, the band CCL kernels, rectangles, Hough vote)
+   of the last collected batch: CUDA events recorded on the launching stream on both sides of the launch - also inside
+   the captured graph of the production path - so the durations are measured live, with the other streams running.
+   index = 0 .. 11 (6 kernels x 2 passes); ms is summed over the batch parts, launches = number of parts.
+   Returns LFD_E_ARG past the last index. */
+int lfd_get_kernel_times(lfd_handle* h, int index, const char** name, int* pass, float* ms, int* launches);
 const char* lfd_timing_name(int i);
 /* Developer aid: with LFD_KTIMING=1 in the environment at lfd_create time every launch is followed by a CUDA
  * event; returns (source line in lfd_b200.cu, ms) per launch of the last run. */
@@ -241,6 +249,19 @@ int lfd_fits_load_frame(const char* path, void* dest, int height, int width, con
 int lfd_catalog_rects(const char* path, int band, int height, int width, double cap, double maxmagdiff,
                       double magcount, double pixscale, long long defaultxy, double maxxy, int32_t* rects,
                       int max_rects, int* n_rects);
+
+/* lfd_ingest_batch: both readers for a whole GPU batch on a pool of `nthreads` native threads (0 = one per hardware
+ * thread) - what the frame loop of DetectTrails.process does per frame before the pixel work
+ * (lfd/detecttrails/detecttrails.py:73-117 and lfd/detecttrails/removestars.py:96-231), batched.  Frame i's raw payload
+ * goes to staging + i * height * width * 4 (e.g. lfd_host_frames), its rectangles to rects + i * max_rects * 4 (count in
+ * n_rects[i]), its header cards to values + (i * nkeys + k) * 72; bands[i] = 0..4 (ugriz) selects filter_caps[bands[i]].
+ * status_frame[i] / status_cat[i] carry the per-item result of lfd_fits_load_frame / lfd_catalog_rects: an item that is
+ * not LFD_OK is left to the caller's general reader, the others are ready for lfd_submit(..., LFD_INPUT_BIGENDIAN). */
+int lfd_ingest_batch(void* staging, int height, int width, int n, const char* const* frame_paths,
+                     const char* const* cat_paths, const int32_t* bands, const double* filter_caps, double maxmagdiff,
+                     double magcount, double pixscale, long long defaultxy, double maxxy, const char* const* keys, int nkeys,
+                     char* values, int32_t* rects, int max_rects, int32_t* n_rects, int32_t* status_frame,
+                     int32_t* status_cat, int nthreads);
 /* Work counters of the last run, summed over the batch: [0] nonzero px voted equ, [1] box, [2] votes,
  * [3] runs fg, [4] runs bg, [5] contours, [6] passing rects, [7] frames that ran dim, [8] frames that ran Hough. */
 int lfd_get_counters(lfd_handle* h, int64_t* out, int n);

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 LFD_OK, LFD_E_ARG, LFD_E_CUDA, LFD_E_UNSUPPORTED, LFD_E_CAPACITY, LFD_E_STATE = 0, -1, -2, -3, -4, -5
 FRAME_OVERFLOW, FRAME_NO_LINES_EQU, FRAME_NO_LINES_BOX = 1, 2, 4
 PASS_BRIGHT, PASS_DIM = 0, 1
-INPUT_NATIVE, INPUT_BIGENDIAN, KEEP_TAPS, FULL_LINES, SERIAL_PASSES = 0, 1, 2, 4, 8
+INPUT_NATIVE, INPUT_BIGENDIAN, KEEP_TAPS, FULL_LINES, SERIAL_PASSES, KERNEL_TIMES = 0, 1, 2, 4, 8, 16
 MAX_SET_LINES = 16
 
 STAGES = {"mask": 0, "gray": 1, "equ": 2, "eroded": 3, "morph": 4, "canny": 5, "box": 6, "hist": 7, "lut": 8,
@@ -122,6 +122,8 @@ def lib():
                                             ctypes.c_double, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.lfd_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.lfd_get_kernel_times.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
         L.lfd_timer_mark.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.lfd_timer_elapsed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         L.lfd_fits_load_frame.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
@@ -129,6 +131,11 @@ def lib():
         L.lfd_catalog_rects.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_longlong,
                                         ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.lfd_ingest_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                       ctypes.POINTER(ctypes.c_char_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_double, ctypes.c_longlong, ctypes.c_double,
+                                       ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         if L.lfd_abi_version() != 1:
             raise ImportError("liblfd_b200.so ABI mismatch")
         _lib = L
@@ -170,6 +177,47 @@ def catalog_rects(path, _filter, shape, defaultxy, filter_caps, maxxy, pixscale,
     if rc != LFD_OK:
         return None
     return out[:n.value].copy() if n.value * 4 < cap else out[:n.value]
+
+
+class BatchIngest:
+    """Result of ``ingest_batch``: per-frame status of the frame / catalog reader (0 = done natively), the raw header
+    card texts, and the blot rectangles (``rects[i, :n_rects[i]]``)."""
+    __slots__ = ("status_frame", "status_cat", "values", "rects", "n_rects", "nkeys")
+
+    def header(self, i):
+        raw = self.values.raw
+        base = 72 * self.nkeys * i
+        return {k: raw[base + 72 * j:base + 72 * j + 72].split(b"\0", 1)[0].decode("ascii", errors="replace")
+                for j, k in enumerate(HEADER_KEYS)}
+
+
+def ingest_batch(staging, frame_paths, cat_paths, filters, defaultxy, filter_caps, maxxy, pixscale, magcount, maxmagdiff,
+                 debug=False, max_rects=8192, nthreads=0):
+    """lfd_ingest_batch: frames into ``staging[i]`` (rows of a handle's pinned buffer viewed as 4-byte items, shape
+    (B, H, W)), catalogs into rectangles, on native threads with the GIL released.  Returns a BatchIngest, or None when
+    the parameters cannot be expressed natively (the caller then loads frame by frame)."""
+    n = len(frame_paths)
+    try:
+        bands = np.array([_BANDS.index(f) for f in filters], np.int32)
+        caps = np.array([float(filter_caps[b]) for b in _BANDS], np.float64)
+        args = (float(maxmagdiff), float(magcount), float(pixscale), int(defaultxy), float(maxxy))
+    except (ValueError, TypeError, KeyError, OverflowError):
+        return None
+    out = BatchIngest()
+    out.nkeys = len(HEADER_KEYS)
+    out.values = ctypes.create_string_buffer(72 * out.nkeys * max(n, 1))
+    out.rects = np.empty((max(n, 1), max_rects, 4), np.int32)
+    out.n_rects = np.zeros(max(n, 1), np.int32)
+    out.status_frame = np.full(max(n, 1), LFD_E_ARG, np.int32)
+    out.status_cat = np.full(max(n, 1), LFD_E_ARG, np.int32)
+    fp = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) if p else None for p in frame_paths])
+    cp = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) if p else None for p in cat_paths])
+    rc = lib().lfd_ingest_batch(staging.ctypes.data_as(ctypes.c_void_p), int(staging.shape[1]), int(staging.shape[2]), n, fp, cp,
+                                bands.ctypes.data_as(ctypes.c_void_p), caps.ctypes.data_as(ctypes.c_void_p), args[0], args[1], args[2],
+                                args[3], args[4], _KEYS_C, out.nkeys, out.values, out.rects.ctypes.data_as(ctypes.c_void_p), max_rects,
+                                out.n_rects.ctypes.data_as(ctypes.c_void_p), out.status_frame.ctypes.data_as(ctypes.c_void_p),
+                                out.status_cat.ctypes.data_as(ctypes.c_void_p), int(nthreads))
+    return out if rc == LFD_OK else None
 
 
 def _kernel_hw(kernel, name):
@@ -315,6 +363,12 @@ class Handle:
         self._keep = None
         return [self._results[i] for i in range(self._n)]
 
+    def wait_array(self):
+        """lfd_wait, results as a NumPy structured array (a copy; fields named like lfd_result) for vectorised decoding."""
+        self._ck(self._L.lfd_wait(self.h, ctypes.byref(self._results)))
+        self._keep = None
+        return np.frombuffer(self._results, dtype=np.dtype(Result), count=self._n).copy()
+
     def run_pass(self, pass_, img, flags=0, writeback=True):
         if img.dtype != np.float32 or not img.flags["C_CONTIGUOUS"] or img.shape != (self.H, self.W):
             raise ValueError("img must be a C-contiguous float32 array of shape (%d, %d)" % (self.H, self.W))
@@ -365,14 +419,15 @@ class Handle:
         Hh, Ww = img.shape
         na, nr = ctypes.c_int(), ctypes.c_int()
         self._L.lfd_hough_dims(Hh, Ww, float(rho), float(theta), ctypes.byref(na), ctypes.byref(nr))
-        cap = na.value * nr.value if max_lines is None else max_lines
-        lines = np.empty((cap, 2), np.float32)
+        cap = na.value * nr.value if max_lines is None else max_lines       # max_lines=0: count + accumulator only, no sort
+        lines = np.empty((max(cap, 1), 2), np.float32)
         accum = np.empty((na.value + 2, nr.value + 2), np.int32) if want_accum else None
         n = ctypes.c_int()
         self._ck(self._L.lfd_hough_lines(self.h, img.ctypes.data_as(ctypes.c_void_p), Hh, Ww, float(rho), float(theta),
-                                         int(threshold), lines.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n),
+                                         int(threshold), lines.ctypes.data_as(ctypes.c_void_p) if cap else None, cap, ctypes.byref(n),
                                          accum.ctypes.data_as(ctypes.c_void_p) if want_accum else None))
         k = min(n.value, cap)
+        self.last_n_lines = n.value
         return (lines[:k].reshape(k, 1, 2).copy() if k else None), accum
 
     def canny(self, img, low, high):
@@ -408,11 +463,25 @@ class Handle:
         self._ck(self._L.lfd_get_timings(self.h, ms, 32, ctypes.byref(n)))
         return [(self._L.lfd_timing_name(i).decode(), float(ms[i])) for i in range(n.value)]
 
+    def kernel_times(self):
+        """[(kernel name, pass, ms summed over the batch parts, launches)] of the bracketed kernels of the last batch."""
+        out = []
+        i = 0
+        while True:
+            name, p, ms, n = ctypes.c_char_p(), ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
+            if self._L.lfd_get_kernel_times(self.h, i, ctypes.byref(name), ctypes.byref(p), ctypes.byref(ms), ctypes.byref(n)) != LFD_OK:
+                break
+            if n.value:
+                out.append((name.value.decode(), p.value, float(ms.value), n.value))
+            i += 1
+        return out
+
     def counters(self):
         c = (ctypes.c_int64 * 16)()
         self._ck(self._L.lfd_get_counters(self.h, c, 16))
         names = ["nnz_equ", "nnz_box", "votes", "runs_fg", "runs_bg", "contours", "passing_rects", "frames_dim",
-                 "frames_hough", "frames_bright_run", "frames_dim_run", "rects_warp_path", "rects_thread_overflow"]
+                 "frames_hough", "frames_bright_run", "frames_dim_run", "rects_warp_path", "rects_thread_overflow",
+                 "hough_smem_atomics"]
         return {k: int(c[i]) for i, k in enumerate(names)}
 
     def timer_mark(self, slot):

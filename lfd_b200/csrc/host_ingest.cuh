@@ -28,7 +28,9 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lfd_b200.h"
@@ -310,4 +312,58 @@ extern "C" int lfd_catalog_rects(const char* path, int band, int height, int wid
         return LFD_OK;
     }
     return LFD_E_UNSUPPORTED;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lfd_ingest_batch: the two readers above for a whole batch of frames, on a pool of native threads.
+// One call per GPU batch replaces 2 x n interpreter round trips of the drop-in driver (lfd_b200/detecttrails.py): the
+// caller hands over the n frame / photoObj paths, the frames land in consecutive slots of `staging` (the handle's pinned
+// host buffer: slot i = staging + i * height * width * 4 bytes) as raw big-endian payload, the blot rectangles in
+// rects[i * max_rects ..], the header cards of the results line in values[(i * nkeys + k) * 72].  Every item reports its
+// own status (LFD_OK, or the code that makes the caller take its general reader for THAT item only), so one odd file
+// does not slow the batch down.  Work items (n frame reads, n catalog reads) are claimed from one atomic counter;
+// the frame reads are what takes time (12.2 MB each from the page cache), so they are claimed first.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int lfd_ingest_batch(void* staging, int height, int width, int n, const char* const* frame_paths,
+                                const char* const* cat_paths, const int32_t* bands, const double* filter_caps,
+                                double maxmagdiff, double magcount, double pixscale, long long defaultxy, double maxxy,
+                                const char* const* keys, int nkeys, char* values, int32_t* rects, int max_rects,
+                                int32_t* n_rects, int32_t* status_frame, int32_t* status_cat, int nthreads)
+{
+    if (!staging || n < 0 || !frame_paths || !cat_paths || !bands || !filter_caps || !rects || !n_rects || !status_frame ||
+        !status_cat || height < 1 || width < 1 || max_rects < 0 || nkeys < 0 || (nkeys > 0 && (!keys || !values))) return LFD_E_ARG;
+    if (n == 0) return LFD_OK;
+    const size_t slot_bytes = (size_t)height * (size_t)width * 4;
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int t = next.fetch_add(1, std::memory_order_relaxed);
+            if (t >= 2 * n) return;
+            if (t < n) {
+                const int i = t;
+                status_frame[i] = frame_paths[i] ? lfd_fits_load_frame(frame_paths[i], (char*)staging + (size_t)i * slot_bytes, height, width,
+                                                                         keys, nkeys, values + (size_t)i * nkeys * 72)
+                                                 : LFD_E_ARG;
+            } else {
+                const int i = t - n;
+                n_rects[i] = 0;
+                const int b = bands[i];
+                status_cat[i] = (cat_paths[i] && b >= 0 && b <= 4)
+                                    ? lfd_catalog_rects(cat_paths[i], b, height, width, filter_caps[b], maxmagdiff, magcount, pixscale,
+                                                        defaultxy, maxxy, rects + (size_t)i * max_rects * 4, max_rects, &n_rects[i])
+                                    : LFD_E_ARG;
+            }
+        }
+    };
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 2 * n) nt = 2 * n;
+    if (nt > 64) nt = 64;
+    std::vector<std::thread> pool;
+    pool.reserve(nt - 1);
+    for (int k = 1; k < nt; k++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return LFD_OK;
 }

@@ -53,11 +53,30 @@ k_hough_compact(const u32* __restrict__ nzmask, const u32* __restrict__ boxmask,
 // smem accumulator row stride: odd, so that lanes (= angles) voting for similar rho hit different banks
 __host__ __device__ inline int hough_rss(int RS) { return RS | 1; }
 
+// r = cvRound(x * cos + y * sin) exactly as OpenCV's float expression (separate roundings, round-half-even).
+// MAGIC: the two conversions run on the FP32 pipe instead of the quarter-rate XU pipe (I2F / F2I), bit-identically:
+//   (float)x      = as_float(0x4B000000 + x) - 2^23          exact for 0 <= x < 2^23
+//   rint(v) (RNE) = as_int(v + 1.5 * 2^23) - 0x4B400000      exact for |v| < 2^22 (the sum lands in [2^23, 2^24), where the
+//                                                            float grid is the integers and FADD rounds half to even)
+// The host selects MAGIC when the frame and rho keep both ranges (hough_magic_ok); otherwise the cvt instructions.
+template <bool MAGIC>
+__device__ __forceinline__ int hough_r(int x, float c, float ys)
+{
+    if (MAGIC) {
+        const float xf = __fsub_rn(__int_as_float(0x4B000000 + x), 8388608.0f);
+        const float v = __fadd_rn(__fmul_rn(xf, c), ys);
+        return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
+    }
+    return __float2int_rn(__fadd_rn(__fmul_rn((float)x, c), ys));
+}
+__host__ inline bool hough_magic_ok(int H, int W, float rho) { return W < (1 << 23) && (double)(W + H) / rho < 4194300.0; }
+
 // grid = (chunks, ngroups, 2*n); dynamic smem = apc * hough_rss(RS) * 4 bytes
+template <bool MAGIC>
 __global__ void __launch_bounds__(HOUGH_THREADS)
 k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const float* __restrict__ tabSin,
              const float* __restrict__ tabCos, const FrameCtl* __restrict__ ctl, int pass, HoughCfg hc,
-             size_t seg_stride, size_t accum_stride)
+             size_t seg_stride, size_t accum_stride, unsigned long long* __restrict__ counters)
 {
     extern __shared__ int acc[];
     int f = blockIdx.z >> 1, which = blockIdx.z & 1;
@@ -65,12 +84,25 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     int nseg = ctl[f].nseg[which];
     // lanes = angles; when apc < 32 the warp covers 32/apc segments at once
     const int per = (hc.apc >= 32) ? 1 : (32 / hc.apc);
-    // Every CTA zeroes and flushes apc x RSS accumulator cells whatever it votes, so a frame gets only as many of
-    // the gridDim.x CTAs as its segment list can keep busy (>= HOUGH_MIN_SEGS each): the box image has ~10x fewer
-    // segments than the morphology output
-    const int nchunks = min((int)gridDim.x, max(1, (nseg + HOUGH_MIN_SEGS - 1) / HOUGH_MIN_SEGS));
-    if ((int)blockIdx.x >= nchunks || nseg == 0) return;
+    // Every CTA zeroes and flushes apc x RSS accumulator cells whatever it votes, so an (image, angle group) gets only
+    // as many of the gridDim.x CTAs (= privatised copies of its accumulator rows) as pay off:
+    //  * >= HOUGH_MIN_SEGS segments each (the box image has ~10x fewer segments than the morphology output);
+    //  * >= 8 votes per accumulator cell and copy on average.  At fine rho the rows are long (RS = 7077 at rho = 1 on a
+    //    2048 x 1489 frame) and a copy that receives one or two votes per cell is flushed with as many GLOBAL atomics as
+    //    it absorbed shared-memory ones: 32 copies of a 1.27 M-cell accumulator were 40 M global atomics per image.
+    //  A single copy owns its rows and is flushed with plain stores.
     const int RSS = hough_rss(hc.RS);
+    const int nnz = ctl[f].nnz[which];
+    int nchunks = min((int)gridDim.x, max(1, (nseg + HOUGH_MIN_SEGS - 1) / HOUGH_MIN_SEGS));
+    //  * but at least enough copies to put ~2 CTAs on every SM when few images are in flight (the single-image entry
+    //    point lfd_hough_lines; a batch has 2 x frames images in gridDim.z and never needs this)
+    {
+        const int by_seg = nchunks;
+        const int by_votes = max(1, nnz / (8 * RSS));
+        const int by_par = (296 + hc.ngroups * (int)gridDim.z - 1) / (hc.ngroups * (int)gridDim.z);
+        nchunks = min(by_seg, max(by_votes, by_par));
+    }
+    if ((int)blockIdx.x >= nchunks || nseg == 0) return;
     int g = blockIdx.y;
     int a0 = g * hc.apc;
     int na = min(hc.apc, hc.numangle - a0);
@@ -88,19 +120,31 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     const float inv_c = (c != 0.f) ? __frcp_rn(c) : 0.f;      // only used to predict bin boundaries (then verified)
     const int off = (hc.numrho - 1) / 2 + 1;
     int* row = acc + a * RSS + off;
-#define HOUGH_R(xx) __float2int_rn(__fadd_rn(__fmul_rn((float)(xx), c), ys))
-    for (int si = warp * per; si < nseg; si += nwarps * per) {
-        int idx = si + sub;
-        if (!live || idx >= nseg) continue;
-        uint2 sgv = sg[idx];
+    int natom = 0;                 // shared-memory atomics this thread issued (counters[13])
+#define HVOTE(bin, w) do { atomicAdd(&row[bin], w); natom++; } while (0)
+#define HOUGH_R(xx) hough_r<MAGIC>((xx), c, ys)
+    // The segment list is read two iterations ahead: an iteration is a dependent chain behind one 8-byte load (L2
+    // latency ~600 cycles against ~100 cycles of work), so without the prefetch the kernel waits on memory.
+    const int step = nwarps * per;
+    auto fetch = [&](int si) -> uint2 {
+        const int idx = si + sub;
+        return (live && idx < nseg) ? __ldg(sg + idx) : make_uint2(0u, 0u);
+    };
+    uint2 q0 = fetch(warp * per), q1 = fetch(warp * per + step);
+    for (int si = warp * per; si < nseg; si += step) {
+        const uint2 sgv = q0;
+        q0 = q1;
+        q1 = fetch(si + 2 * step);
+        if (sgv.y == 0u) continue;                  // lane has no segment in this iteration (mask words are never zero)
         int y = sgv.x >> 16, x0 = (sgv.x & 0xffff) << 5;
         u32 m = sgv.y;
-        float ys = __fmul_rn((float)y, s);
+        const float yf = MAGIC ? __fsub_rn(__int_as_float(0x4B000000 + y), 8388608.0f) : (float)y;
+        float ys = __fmul_rn(yf, s);
         int fb = __ffs(m) - 1, lb = 31 - __clz(m);
         int r1 = HOUGH_R(x0 + fb);
         int r2 = HOUGH_R(x0 + lb);
         if (r1 == r2) {
-            atomicAdd(&row[r1], __popc(m));
+            HVOTE(r1, __popc(m));
         } else if (abs(r2 - r1) <= 2 && __popc(m) > 4) {
             // r is monotone in x: locate the (at most two) bin boundaries inside the word.  The crossing of
             // r + 0.5 (towards r2) is predicted from the real-valued line x = (r +- 0.5 - y sin) / cos, the exact
@@ -110,7 +154,9 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
             const float half = (r2 > r1) ? 0.5f : -0.5f;
             auto last_with = [&](int lo, int hi, int rr) -> int {       // R(lo) == rr, R(hi) != rr  ->  largest x with R(x) == rr
                 const float xg = __fmul_rn(__fsub_rn(__fadd_rn((float)rr, half), ys), inv_c) - (float)x0;
-                int g = min(max(__float2int_rd(xg), lo), hi - 1);
+                // (a prediction only - any integer works, it is verified below - so the conversion may be the magic one too)
+                int g = MAGIC ? (__float_as_int(__fadd_rn(xg, 12582912.0f)) - 0x4B400000) : __float2int_rd(xg);
+                g = min(max(g, lo), hi - 1);
                 if (HOUGH_R(x0 + g) == rr) lo = g; else hi = g;
                 if (hi - lo > 1) {
                     g = (lo == g) ? g + 1 : g - 1;
@@ -124,15 +170,15 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
             };
             const int lo = last_with(fb, lb, r1), hi = lo + 1;
             int c1 = __popc(m & bit_range(fb, lo));
-            atomicAdd(&row[r1], c1);
+            HVOTE(r1, c1);
             int rm = HOUGH_R(x0 + hi);
             if (rm == r2) {
-                atomicAdd(&row[r2], __popc(m & bit_range(hi, lb)));
+                HVOTE(r2, __popc(m & bit_range(hi, lb)));
             } else {
                 const int lo2 = last_with(hi, lb, rm), hi2 = lo2 + 1;
                 int c2 = __popc(m & bit_range(hi, lo2));
-                if (c2) atomicAdd(&row[rm], c2);
-                atomicAdd(&row[r2], __popc(m & bit_range(hi2, lb)));
+                if (c2) HVOTE(rm, c2);
+                HVOTE(r2, __popc(m & bit_range(hi2, lb)));
             }
         } else {
             int cur = r1, cnt = 1;
@@ -142,20 +188,24 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
                 m &= m - 1;
                 int r = HOUGH_R(x0 + b);
                 if (r == cur) cnt++;
-                else { atomicAdd(&row[cur], cnt); cur = r; cnt = 1; }
+                else { HVOTE(cur, cnt); cur = r; cnt = 1; }
             }
-            atomicAdd(&row[cur], cnt);
+            HVOTE(cur, cnt);
         }
     }
 #undef HOUGH_R
+#undef HVOTE
+    for (int o = 16; o; o >>= 1) natom += __shfl_xor_sync(FULLMASK, natom, o);
+    if (lane == 0 && natom && counters) atomicAdd(&counters[13], (unsigned long long)natom);
     __syncthreads();
     int* gacc = accum + ((size_t)f * 2 + which) * accum_stride;
     for (int aa = threadIdx.x >> 5; aa < na; aa += HOUGH_THREADS / 32) {        // one warp per angle row: no division
         const int* arow = acc + aa * RSS;
         int* grow = gacc + (size_t)(a0 + aa + 1) * hc.RS;
-        for (int col = lane; col < RSS; col += 32) {
-            const int v = arow[col];
-            if (v) atomicAdd(&grow[col], v);
+        if (nchunks == 1) {
+            for (int col = lane; col < RSS; col += 32) { const int v = arow[col]; if (v) grow[col] = v; }      // sole owner of the row
+        } else {
+            for (int col = lane; col < RSS; col += 32) { const int v = arow[col]; if (v) atomicAdd(&grow[col], v); }
         }
     }
 }

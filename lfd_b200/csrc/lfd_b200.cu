@@ -28,6 +28,7 @@ static std::string g_create_error;
 
 // dynamic shared-memory opt-in (cudaFuncSetAttribute) is per function AND per device: high-water marks per device
 #define LFD_MAX_DEVICES 64
+#define LFD_MAX_SPLIT 4
 struct DevLimits { size_t band_max = 48 * 1024, rects_max = 48 * 1024, anyk_max = 48 * 1024; };
 static DevLimits g_dev_limits[LFD_MAX_DEVICES];
 
@@ -41,6 +42,13 @@ static const char* k_timing_names[] = {
     "dim:rects+boxfill", "dim:hough", "dim:check_theta",
     "results_d2h"};
 #define N_TIMINGS 17
+
+// Brackets: a CUDA event on each side of the launches that carry the step (recorded on the launching stream, also
+// inside the captured graph), so that bench.py can quote the average launch duration of the time-dominant kernel
+// measured live in the timed region (lfd_get_kernel_times).
+enum { KB_MORPH = 0, KB_NMS, KB_CCL_BAND_FG, KB_CCL_BAND_BG, KB_RECTS, KB_HOUGH_VOTE, KB_COUNT };
+static const char* k_bracket_names[KB_COUNT] = {"k_morph_march", "k_nms_march", "k_ccl_band(fg)", "k_ccl_band(bg)",
+                                                "k_rects_warp", "k_hough_vote"};
 
 struct HoughBufs {
     HoughCfg hc;
@@ -61,9 +69,12 @@ struct lfd_handle {
     lfd_params params;
     bool have_params = false;
     cudaStream_t stream = nullptr;        // uploads, prep, bright pass, results
-    cudaStream_t stream2 = nullptr;       // dim pass, overlapped with the bright pass
-    cudaStream_t stream3 = nullptr, stream4 = nullptr;   // second half of the batch (bright, dim)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+    // the batch is cut in `nsplit` parts; part k runs its bright pass on xs[k][0] and its dim pass on xs[k][1]
+    // (xs[0][0] is `stream` itself); every extra stream joins `stream` through its own event
+    cudaStream_t xs[LFD_MAX_SPLIT][2];
+    cudaEvent_t xjoin[LFD_MAX_SPLIT][2];
+    cudaEvent_t ev_fork = nullptr;
+    int nsplit_cfg = 2;                   // env LFD_NSPLIT (1..LFD_MAX_SPLIT)
     std::string err;
     int64_t launches = 0;
     int last_n = 0, last_flags = 0;
@@ -112,6 +123,11 @@ struct lfd_handle {
     cudaEvent_t ev[N_TIMINGS + 1];
     bool ev_valid[N_TIMINGS + 1];
     float timings[N_TIMINGS];
+    cudaEvent_t kb[LFD_MAX_SPLIT][2][KB_COUNT][2];    // [part][pass][kernel][begin / end], created on first use
+    bool kb_used[LFD_MAX_SPLIT][2][KB_COUNT];         // recorded by the last run
+    float kb_ms[2][KB_COUNT];                         // last run: per pass, summed over the parts
+    int kb_launches[2][KB_COUNT];
+    int cur_part = 0;                                 // part index of the run_pass_kernels call in progress
     // CUDA graph of the two passes + verdict + result copies (whole-frame path without taps): ~100 small launches
     // become one graph launch, which removes the per-launch gaps between the latency-bound kernels
     bool use_graphs = true;
@@ -316,7 +332,8 @@ static int hough_setup(lfd_handle* h, HoughBufs* hb, int H, int W, double rho_, 
     CK(cudaMemcpyAsync(hb->tabCos, tc.data(), hc.numangle * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     // the limit is per function, not per launch: both passes (and lfd_hough_lines) share k_hough_vote
-    CK(cudaFuncSetAttribute(k_hough_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
+    CK(cudaFuncSetAttribute(k_hough_vote<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
+    CK(cudaFuncSetAttribute(k_hough_vote<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
     return LFD_OK;
 }
 
@@ -332,9 +349,9 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (!h) return LFD_E_ARG;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->stream2) cudaStreamSynchronize(h->stream2);
-    if (h->stream3) cudaStreamSynchronize(h->stream3);
-    if (h->stream4) cudaStreamSynchronize(h->stream4);
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++)
+            if (h->xs[k][p] && h->xs[k][p] != h->stream) cudaStreamSynchronize(h->xs[k][p]);
     for (void* p : h->allocs) cudaFree(p);
     for (int p = 0; p < 2; p++) {
         if (h->hb[p].accum) cudaFree(h->hb[p].accum);
@@ -349,15 +366,19 @@ extern "C" int lfd_destroy(lfd_handle* h)
     if (h->ctl_h) cudaFreeHost(h->ctl_h);
     if (h->counters_h) cudaFreeHost(h->counters_h);
     for (int i = 0; i <= N_TIMINGS; i++) if (h->ev_valid[i]) cudaEventDestroy(h->ev[i]);
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++)
+            for (int b = 0; b < KB_COUNT; b++)
+                for (int e = 0; e < 2; e++)
+                    if (h->kb[k][p][b][e]) cudaEventDestroy(h->kb[k][p][b][e]);
     for (int i = 0; i < 4; i++) if (h->mark_valid[i]) cudaEventDestroy(h->mark[i]);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
-    if (h->ev_join4) cudaEventDestroy(h->ev_join4);
-    if (h->stream4) cudaStreamDestroy(h->stream4);
-    if (h->stream3) cudaStreamDestroy(h->stream3);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++) {
+            if (h->xjoin[k][p]) cudaEventDestroy(h->xjoin[k][p]);
+            if (h->xs[k][p] && h->xs[k][p] != h->stream) cudaStreamDestroy(h->xs[k][p]);
+        }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return LFD_OK;
@@ -386,13 +407,14 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     long long worst = (long long)H * ((W + 1) / 2);
     if (h->cfg.max_runs > worst) h->cfg.max_runs = (int)worst;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++) {
+            if (k == 0 && p == 0) { h->xs[0][0] = h->stream; continue; }
+            CK(cudaStreamCreateWithFlags(&h->xs[k][p], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->xjoin[k][p], cudaEventDisableTiming));
+        }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    { const char* ns = getenv("LFD_NSPLIT"); if (ns && ns[0] >= '1' && ns[0] <= '0' + LFD_MAX_SPLIT) h->nsplit_cfg = ns[0] - '0'; }
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
@@ -422,6 +444,10 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
     }
     for (int i = 0; i <= N_TIMINGS; i++) { CK(cudaEventCreate(&h->ev[i])); h->ev_valid[i] = true; }
     for (int i = 0; i < 4; i++) { CK(cudaEventCreate(&h->mark[i])); h->mark_valid[i] = true; }
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++)
+            for (int b = 0; b < KB_COUNT; b++)
+                for (int e = 0; e < 2; e++) CK(cudaEventCreate(&h->kb[k][p][b][e]));
 
     const int B = h->B;
     const size_t N = h->d.N, NW = h->d.NW;
@@ -693,7 +719,16 @@ extern "C" int lfd_set_kernels(lfd_handle* h, int pass, const uint8_t* erode_mas
 static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, cudaStream_t s, bool stage_events, int part = 0)
 {
 #define STAGE_EVENT(i) do { if (stage_events) CK(cudaEventRecord(h->ev[i], s)); } while (0)
+#define KB_MARK(id, e) do {                                                                          \
+        if (!(flags & LFD_KERNEL_TIMES)) break;                                                        \
+        cudaEvent_t& kev_ = h->kb[h->cur_part][pass][id][e];                                           \
+        /* under stream capture a plain record is a dependency marker, not a node: ask for an external record node */ \
+        CK(cudaEventRecordWithFlags(kev_, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault)); \
+        h->kb_used[h->cur_part][pass][id] = true;                                                      \
+    } while (0)
     const Dims d = h->d;
+    bool capturing = false;
+    { cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone; if (cudaStreamIsCapturing(s, &cst) == cudaSuccess) capturing = cst == cudaStreamCaptureStatusActive; }
     const lfd_pass_params& pp = pass ? h->params.dim : h->params.bright;
     FrameCtl* const C = h->ctl + (size_t)pass * h->B + f0;      // this pass's bookkeeping block
     const size_t fN = (size_t)f0 * d.N, fNW = (size_t)f0 * d.NW;
@@ -734,6 +769,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         if (!h->eroded_tap) { int rc = dev_alloc(h, &h->eroded_tap, (size_t)h->B * d.N); if (rc) return rc; }
         etap = h->eroded_tap + fN;
     }
+    KB_MARK(KB_MORPH, 0);
     {
         const u8* lutp = h->lut + ((size_t)pass * h->B + f0) * 256;
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + MARCH_R - 1) / MARCH_R;
@@ -780,10 +816,12 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         }
         LAUNCH_CHECK();
     }
+    KB_MARK(KB_MORPH, 1);
     STAGE_EVENT(tbase + 1);
     }
-    // Sobel + NMS (already done by the fused kernel on the production path)
+    // Sobel + NMS (done by the fused kernel when that is selected)
     if (!fused) {
+    KB_MARK(KB_NMS, 0);
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
@@ -795,12 +833,15 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
         k_canny_nms<<<cg, 256, 0, s>>>(v_morph, v_nz, v_cand, v_strong, ntap, C, pass, d, 0, 255);
     }
     LAUNCH_CHECK();
+    KB_MARK(KB_NMS, 1);
     }
     STAGE_EVENT(tbase + 2);
     // foreground runs: hysteresis + outer contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl0, C, pass, d, 0, h->cfg.max_runs); LAUNCH_CHECK();
+    KB_MARK(KB_CCL_BAND_FG, 0);
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
+    KB_MARK(KB_CCL_BAND_FG, 1);
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_cand, v_ccl0, C, pass, d, 0); LAUNCH_CHECK();
     const dim3 flat(CCL_FLAT_CTAS, n);
     CK(cudaMemsetAsync(v_edges, 0, (size_t)n * d.NW * sizeof(u32), s));
@@ -811,14 +852,18 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     // background runs: hole contours
     k_ccl_rowcount<<<rows, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_rowscan<<<n, 1024, 0, s>>>(v_ccl1, C, pass, d, 1, h->cfg.max_runs); LAUNCH_CHECK();
+    KB_MARK(KB_CCL_BAND_BG, 0);
     k_ccl_band<<<bands, 256, ccl_band_smem(d.WW), s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
+    KB_MARK(KB_CCL_BAND_BG, 1);
     k_ccl_merge<<<seams, CCL_WARPS * 32, 0, s>>>(v_edges, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_stats_flat<<<flat, 256, 0, s>>>(nullptr, v_ccl1, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_alloc_flat<<<flat, 256, 0, s>>>(v_ccl1, nullptr, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     k_ccl_extremes_flat<<<flat, 256, 0, s>>>(v_edges, v_ccl1, v_comp, C, pass, d, 1); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 4);
     // rectangles + box image
+    KB_MARK(KB_RECTS, 0);
     k_rects_warp<<<h->sm_count * 16, RECT_WARPS * 32, rects_smem(n), s>>>(v_comp, v_rbuf, v_ccl0, v_ccl1, C, pass, n, d, pp.minAreaRectMinLen, pp.lwTresh, (unsigned long long*)h->counters_d, v_edges, pp.contoursMode == 0 ? 1 : 0); LAUNCH_CHECK();
+    KB_MARK(KB_RECTS, 1);
     CK(cudaMemsetAsync(v_box, 0, (size_t)n * d.NW * sizeof(u32), s));
     k_fill_boxes<<<dim3(16, n), 128, 0, s>>>(v_rbuf, v_box, C, pass, d); LAUNCH_CHECK();
     STAGE_EVENT(tbase + 5);
@@ -829,8 +874,15 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     CK(cudaMemsetAsync(v_accum, 0, (size_t)n * 2 * hb.accum_stride * sizeof(int), s));
     // a thread's iterations are a serial chain (load -> ballot -> slot atomic -> store): many CTAs, few iterations each
     k_hough_compact<<<dim3(128, n, 2), 256, 0, s>>>(v_nz, v_box, v_segs, C, pass, d, (size_t)d.NW); LAUNCH_CHECK();
-    k_hough_vote<<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(v_segs, v_accum, hb.tabSin, hb.tabCos, C, pass,
-                                                                            hb.hc, (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
+    KB_MARK(KB_HOUGH_VOTE, 0);
+    if (hough_magic_ok(d.H, d.W, hb.hc.rho))
+        k_hough_vote<true><<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(v_segs, v_accum, hb.tabSin, hb.tabCos, C, pass,
+                                                                                  hb.hc, (size_t)d.NW, hb.accum_stride, (unsigned long long*)h->counters_d);
+    else
+        k_hough_vote<false><<<dim3(32, hb.hc.ngroups, 2 * n), HOUGH_THREADS, hb.smem, s>>>(v_segs, v_accum, hb.tabSin, hb.tabCos, C, pass,
+                                                                                   hb.hc, (size_t)d.NW, hb.accum_stride, (unsigned long long*)h->counters_d);
+    LAUNCH_CHECK();
+    KB_MARK(KB_HOUGH_VOTE, 1);
     int cells = hb.hc.numangle * hb.hc.numrho;
     int pblocks = (cells + 255) / 256; if (pblocks > 64) pblocks = 64;
     k_hough_peaks<<<dim3(pblocks, 2 * n), 256, 0, s>>>(v_accum, v_keys, C, pass, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
@@ -845,6 +897,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     STAGE_EVENT(tbase + 7);
     return LFD_OK;
 #undef STAGE_EVENT
+#undef KB_MARK
 }
 
 // mode 0: whole-frame pipeline on h->in (un-flipped) ; mode 1/2: standalone bright/dim on frame slot 0
@@ -855,6 +908,9 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     if (!h->have_params) { h->err = "lfd_set_params has not been called"; return LFD_E_STATE; }
     CK(cudaMemsetAsync(h->counters_d, 0, 16 * sizeof(int64_t), s));
     CK(cudaEventRecord(h->ev[0], s));
+    const bool replay = h->graph_exec && h->use_graphs && h->graph_n == n && h->graph_flags == flags && mode == 0 &&
+                        !(flags & (LFD_SERIAL_PASSES | LFD_KEEP_TAPS | LFD_FULL_LINES)) && !h->ktiming;
+    if (!replay) memset(h->kb_used, 0, sizeof(h->kb_used));       // a replayed graph records the brackets of its capture again
     if (h->ktiming) { h->kn = 0; ktime_mark(h, 0); }
     k_ctl_init<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode != 2, mode != 1); LAUNCH_CHECK();
     CK(cudaMemsetAsync(h->hist, 0, (size_t)2 * h->B * 256 * sizeof(u32), s));
@@ -901,31 +957,36 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     // two passes overlap almost completely.  LFD_SERIAL_PASSES keeps one stream (clean per-stage timings).
     const bool overlap = mode == 0 && !(flags & LFD_SERIAL_PASSES) && !h->ktiming;
     const bool graph = overlap && h->use_graphs && !(flags & (LFD_KEEP_TAPS | LFD_FULL_LINES));
-    cudaStream_t s1 = overlap ? h->stream2 : s;
     h->stage_timings_valid = !graph;
     // everything from the fork to the result copies; captured into a CUDA graph when `graph`
-    // with overlap and a batch of >= 16 frames the batch is also cut in two halves: four independent chains
-    // (bright / dim x half) keep the SMs busy through the latency-bound CCL / geometry phases
-    const int nsplit = (overlap && n >= 16) ? 2 : 1;
-    const int nh0 = nsplit == 2 ? (n + 1) / 2 : n;
+    // with overlap and a batch of >= 16 frames the batch is also cut in nsplit parts (default two halves): 2 x nsplit
+    // independent chains (bright / dim x part) keep the SMs busy through the latency-bound CCL / geometry phases
+    int nsplit = (overlap && n >= 16) ? h->nsplit_cfg : 1;
+    if (nsplit > 1 && n / nsplit < 8) nsplit = n / 8 > 0 ? n / 8 : 1;
     auto passes = [&](bool stage_events) -> int {
         int rc2;
         if (overlap) {
             CK(cudaEventRecord(h->ev_fork, s));
-            CK(cudaStreamWaitEvent(s1, h->ev_fork, 0));
-            if (nsplit == 2) { CK(cudaStreamWaitEvent(h->stream3, h->ev_fork, 0)); CK(cudaStreamWaitEvent(h->stream4, h->ev_fork, 0)); }
+            for (int k = 0; k < nsplit; k++)
+                for (int p = 0; p < 2; p++)
+                    if (k || p) CK(cudaStreamWaitEvent(h->xs[k][p], h->ev_fork, 0));
         }
-        if (mode != 2) { if ((rc2 = run_pass_kernels(h, 0, nh0, 0, flags, s, stage_events)) != LFD_OK) return rc2; }
-        else for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
-        if (mode != 1) { if ((rc2 = run_pass_kernels(h, 0, nh0, 1, flags, s1, stage_events)) != LFD_OK) return rc2; }
-        else for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
-        if (nsplit == 2) {
-            if ((rc2 = run_pass_kernels(h, nh0, n - nh0, 0, flags, h->stream3, false)) != LFD_OK) return rc2;
-            if ((rc2 = run_pass_kernels(h, nh0, n - nh0, 1, flags, h->stream4, false)) != LFD_OK) return rc2;
-            CK(cudaEventRecord(h->ev_join3, h->stream3)); CK(cudaStreamWaitEvent(s, h->ev_join3, 0));
-            CK(cudaEventRecord(h->ev_join4, h->stream4)); CK(cudaStreamWaitEvent(s, h->ev_join4, 0));
+        int fstart = 0;
+        for (int k = 0; k < nsplit; k++) {
+            const int cnt = (n - fstart + (nsplit - k) - 1) / (nsplit - k);     // first parts take the remainder
+            cudaStream_t sb = overlap ? h->xs[k][0] : s, sd = overlap ? h->xs[k][1] : s;
+            const bool ev = stage_events && k == 0;
+            h->cur_part = k;
+            if (mode != 2) { if ((rc2 = run_pass_kernels(h, fstart, cnt, 0, flags, sb, ev)) != LFD_OK) return rc2; }
+            else if (k == 0) for (int i = 3; i <= T_PER_PASS + 1; i++) CK(cudaEventRecord(h->ev[i], s));
+            if (mode != 1) { if ((rc2 = run_pass_kernels(h, fstart, cnt, 1, flags, sd, ev)) != LFD_OK) return rc2; }
+            else if (k == 0) for (int i = T_PER_PASS + 2; i < N_TIMINGS; i++) CK(cudaEventRecord(h->ev[i], s));
+            fstart += cnt;
         }
-        if (overlap) { CK(cudaEventRecord(h->ev_join, s1)); CK(cudaStreamWaitEvent(s, h->ev_join, 0)); }
+        if (overlap)
+            for (int k = 0; k < nsplit; k++)
+                for (int p = 0; p < 2; p++)
+                    if (k || p) { CK(cudaEventRecord(h->xjoin[k][p], h->xs[k][p])); CK(cudaStreamWaitEvent(s, h->xjoin[k][p], 0)); }
         k_finalize<<<(n + 127) / 128, 128, 0, s>>>(h->ctl, h->B, h->res_d, n, mode, (unsigned long long*)h->counters_d); LAUNCH_CHECK();
         CK(cudaMemcpyAsync(h->res_h, h->res_d, (size_t)n * sizeof(lfd_result), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h->ctl_h, h->ctl, (size_t)n * sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
@@ -1020,7 +1081,30 @@ extern "C" int lfd_wait(lfd_handle* h, lfd_result* out)
             if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
         h->timings[i] = ms;
     }
+    memset(h->kb_ms, 0, sizeof(h->kb_ms));
+    memset(h->kb_launches, 0, sizeof(h->kb_launches));
+    for (int k = 0; k < LFD_MAX_SPLIT; k++)
+        for (int p = 0; p < 2; p++)
+            for (int b = 0; b < KB_COUNT; b++) {
+                if (!h->kb_used[k][p][b]) continue;
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, h->kb[k][p][b][0], h->kb[k][p][b][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+                h->kb_ms[p][b] += ms;
+                h->kb_launches[p][b]++;
+            }
     if (out) memcpy(out, h->res_h, (size_t)h->last_n * sizeof(lfd_result));
+    return LFD_OK;
+}
+
+// Bracketed kernels of the last collected batch: name, pass, summed duration over the batch parts and number of launches.
+extern "C" int lfd_get_kernel_times(lfd_handle* h, int index, const char** name, int* pass, float* ms, int* launches)
+{
+    if (!h || index < 0 || index >= 2 * KB_COUNT) return LFD_E_ARG;
+    const int p = index / KB_COUNT, b = index % KB_COUNT;
+    if (name) *name = k_bracket_names[b];
+    if (pass) *pass = p;
+    if (ms) *ms = h->kb_ms[p][b];
+    if (launches) *launches = h->kb_launches[p][b];
     return LFD_OK;
 }
 
@@ -1211,23 +1295,42 @@ extern "C" int lfd_hough_lines(lfd_handle* h, const uint8_t* img, int height, in
     if (rc != LFD_OK) return rc;
     HoughBufs& hb = hs.hb;
     CK(cudaMemcpyAsync(hs.img, img, (size_t)d.N, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->counters_d, 0, 16 * sizeof(int64_t), s));
     k_ctl_init<<<1, 32, 0, s>>>(hs.ctl, 1, hs.res, 1, 1, 0); LAUNCH_CHECK();
     // mark Hough as enabled for pass 0
     FrameCtl c; memset(&c, 0, sizeof(c)); c.active[0] = 1; c.hough[0] = 1;
     CK(cudaMemcpyAsync(hs.ctl, &c, sizeof(c), cudaMemcpyHostToDevice, s));
+    // device times of the four phases -> lfd_get_timings entries 0..3 (pack+compact, vote, peaks, sort)
+    CK(cudaEventRecord(h->ev[0], s));
     k_pack_mask<<<592, 256, 0, s>>>(hs.img, hs.mask, d); LAUNCH_CHECK();
     CK(cudaMemsetAsync(hb.accum, 0, (size_t)2 * hb.accum_stride * sizeof(int), s));
     // which = 0 only: pass the same mask twice and ignore slot 1
     k_hough_compact<<<dim3(64, 1, 1), 256, 0, s>>>(hs.mask, hs.mask, hs.segs, hs.ctl, 0, d, (size_t)d.NW); LAUNCH_CHECK();
-    k_hough_vote<<<dim3(32, hb.hc.ngroups, 1), HOUGH_THREADS, hb.smem, s>>>(hs.segs, hb.accum, hb.tabSin, hb.tabCos, hs.ctl, 0, hb.hc,
-                                                                         (size_t)d.NW, hb.accum_stride); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[1], s));
+    if (hough_magic_ok(height, width, hb.hc.rho))
+        k_hough_vote<true><<<dim3(32, hb.hc.ngroups, 1), HOUGH_THREADS, hb.smem, s>>>(hs.segs, hb.accum, hb.tabSin, hb.tabCos, hs.ctl, 0, hb.hc,
+                                                                               (size_t)d.NW, hb.accum_stride, (unsigned long long*)h->counters_d);
+    else
+        k_hough_vote<false><<<dim3(32, hb.hc.ngroups, 1), HOUGH_THREADS, hb.smem, s>>>(hs.segs, hb.accum, hb.tabSin, hb.tabCos, hs.ctl, 0, hb.hc,
+                                                                                (size_t)d.NW, hb.accum_stride, (unsigned long long*)h->counters_d);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[2], s));
     long long cells = (long long)hb.hc.numangle * hb.hc.numrho;
     int pblocks = (int)((cells + 255) / 256); if (pblocks > 1184) pblocks = 1184;
     k_hough_peaks<<<dim3(pblocks, 1), 256, 0, s>>>(hb.accum, hb.keys, hs.ctl, 0, hb.hc, hb.accum_stride, hb.key_stride); LAUNCH_CHECK();
-    k_hough_sort<<<dim3(1, 1), 1024, 0, s>>>(hb.keys, hb.lines, hs.ctl, 0, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[3], s));
+    // the full sort is only needed when the caller wants the line list (n_lines and the accumulator do not depend on it)
+    if (lines && max_lines > 0) { k_hough_sort<<<dim3(1, 1), 1024, 0, s>>>(hb.keys, hb.lines, hs.ctl, 0, hb.hc, hb.key_stride, hb.line_stride, hb.max_lines); LAUNCH_CHECK(); }
+    CK(cudaEventRecord(h->ev[4], s));
     FrameCtl out;
     CK(cudaMemcpyAsync(&out, hs.ctl, sizeof(out), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->counters_h, h->counters_d, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    memset(h->timings, 0, sizeof(h->timings));
+    for (int i = 0; i < 4; i++)
+        if (cudaEventElapsedTime(&h->timings[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) { h->timings[i] = 0.f; cudaGetLastError(); }
+    h->counters_h[0] = out.nnz[0];
+    h->counters_h[2] = (int64_t)out.nnz[0] * hb.hc.numangle;
     int np = out.npeaks[0];
     if (n_lines) *n_lines = np;
     int ncopy = np < max_lines ? np : max_lines;
@@ -1251,6 +1354,8 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     FrameCtl* const C = h->ctl;
     CK(cudaMemcpyAsync(h->morph[pass], img, (size_t)d.N, cudaMemcpyHostToDevice, s));
     k_ctl_init<<<1, 32, 0, s>>>(h->ctl, h->B, h->res_d, 1, 1, 0); LAUNCH_CHECK();
+    // device times -> lfd_get_timings entries 0..1 (Sobel + NMS incl. the input mask, hysteresis by run CCL)
+    CK(cudaEventRecord(h->ev[0], s));
     k_pack_mask<<<592, 256, 0, s>>>(h->morph[pass], h->nz[pass], d); LAUNCH_CHECK();
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
@@ -1262,6 +1367,7 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
         k_canny_nms<<<cg, 256, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d, low, high);
     }
     LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[1], s));
     dim3 rows((d.H + CCL_WARPS * CCL_RC_ROWS - 1) / (CCL_WARPS * CCL_RC_ROWS), n);
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
     dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
@@ -1272,11 +1378,15 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     CK(cudaMemsetAsync(h->edges[pass], 0, (size_t)d.NW * sizeof(u32), s));
     k_ccl_stats_flat<<<dim3(CCL_FLAT_CTAS, n), 256, 0, s>>>(h->strong[pass], h->ccl_d[pass][0], C, pass, d, 0); LAUNCH_CHECK();
     k_ccl_alloc_flat<<<dim3(CCL_FLAT_CTAS, n), 256, 0, s>>>(h->ccl_d[pass][0], h->edges[pass], h->comp_d[pass], C, pass, d, 0); LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev[2], s));
     k_expand_mask<<<dim3(592, 1), 256, 0, s>>>(h->edges[pass], h->tap_u8, d); LAUNCH_CHECK();
     FrameCtl out;
     CK(cudaMemcpyAsync(&out, C, sizeof(out), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(edges_out, h->tap_u8, (size_t)d.N, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    memset(h->timings, 0, sizeof(h->timings));
+    for (int i = 0; i < 2; i++)
+        if (cudaEventElapsedTime(&h->timings[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) { h->timings[i] = 0.f; cudaGetLastError(); }
     if (out.status & LFD_FRAME_OVERFLOW) { h->err = "edge map has more runs than lfd_config.max_runs"; return LFD_E_CAPACITY; }
     return LFD_OK;
 }
@@ -1305,6 +1415,7 @@ extern "C" int lfd_fit_min_area_rect(lfd_handle* h, const uint8_t* img, int cont
         k_ctl_init<<<1, 32, 0, s>>>(h->ctl, h->B, h->res_d, 1, 1, 0);
         k_pack_mask<<<592, 256, 0, s>>>(h->morph[0], h->nz[0], d);
         h->launches += 2;
+        h->cur_part = 0;
         if ((rc = run_pass_kernels(h, 0, 1, 0, 0, s, false, 1)) != LFD_OK) break;
         k_expand_mask<<<dim3(592, 1), 256, 0, s>>>(h->box[0], h->tap_u8, d);
         h->launches++;

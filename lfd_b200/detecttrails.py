@@ -19,7 +19,7 @@ import numpy as _np
 
 from . import _lib, sdssfiles as files
 from .processfield import result_from_device, setup_debug
-from .removestars import read_photoObj_arrays, star_rects, star_rects_batch
+from .removestars import read_photoObj_arrays, star_rects
 
 try:
     import fitsio
@@ -60,18 +60,25 @@ FORMAT_HEADER_VALUES = False
 def _load_frame(run, camcol, filter, field, raw=False):
     """detecttrails.py:73-117: resolve the path, unpack .bz2 if needed, read image + header.
     Returns (img, header_prefix_of_the_results_line[, big_endian]).  With raw=True and the built-in FITS reader the
-    image is the undecoded big-endian payload (uint32 view) and big_endian is True: the device byte-swaps."""
-    removefits = False
-    fitspath = None
-    try:
-        origfitspath = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
-        if not os.path.exists(origfitspath):
-            bzpath = origfitspath + ".bz2"
-            if not os.path.exists(bzpath):
-                errmsg = ("File {0} or its bz2 compressed version not found. Are you sure they exist?")
-                raise FileNotFoundError(errmsg.format(origfitspath))
-            with open(bzpath, "rb") as compressedfits:
-                fitsdata = bz2.decompress(compressedfits.read())
+    image is the undecoded big-endian payload (uint32 view) and big_endian is True: the device byte-swaps.
+
+    A compressed frame is decompressed in memory with the built-in reader (no FITS_DUMP round trip through the file
+    system: the reference writes the decompressed file, reads it and deletes it, detecttrails.py:90-111 - the pixels and
+    header are the same); with the real ``fitsio`` module, which reads from paths only, the reference's temporary file
+    is kept."""
+    origfitspath = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
+    if not os.path.exists(origfitspath):
+        bzpath = origfitspath + ".bz2"
+        if not os.path.exists(bzpath):
+            errmsg = ("File {0} or its bz2 compressed version not found. Are you sure they exist?")
+            raise FileNotFoundError(errmsg.format(origfitspath))
+        with open(bzpath, "rb") as compressedfits:
+            fitsdata = bz2.decompress(compressedfits.read())          # releases the GIL: loader threads decompress in parallel
+        if hasattr(fitsio, "read_image_bytes"):
+            img, h, big_endian = fitsio.read_image_bytes(fitsdata)
+            if not raw and big_endian:
+                img, big_endian = img.view(">f4").astype(_np.float32), False
+        else:
             try:
                 fitsdmp = os.environ["FITS_DUMP"]
             except KeyError:
@@ -80,27 +87,26 @@ def _load_frame(run, camcol, filter, field, raw=False):
             fitspath = os.path.join(fitsdmp, os.path.split(origfitspath)[-1])
             with open(fitspath, "wb") as decompressed:
                 decompressed.write(fitsdata)
-            removefits = True
-        else:
-            fitspath = origfitspath
+            try:
+                img, h, big_endian = fitsio.read(fitspath), fitsio.read_header(fitspath), False
+            finally:
+                os.remove(fitspath)
+    else:
         big_endian = False
         if raw and hasattr(fitsio, "read_raw_image"):
             try:
-                img, h = fitsio.read_raw_image(fitspath)
+                img, h = fitsio.read_raw_image(origfitspath)
                 big_endian = True
-            except ValueError:           # not a plain BITPIX=-32 image: decode on the host
-                img = fitsio.read(fitspath)
-                h = fitsio.read_header(fitspath)
+            except ValueError:           # not a plain unscaled BITPIX=-32 image: decode on the host
+                img = fitsio.read(origfitspath)
+                h = fitsio.read_header(origfitspath)
         else:
-            img = fitsio.read(fitspath)
-            h = fitsio.read_header(fitspath)
-        if not big_endian and img.dtype != _np.float32:
-            img = img.astype(_np.float32)
-        printit = _results_prefix(run, camcol, filter, field, h)
-        return (img, printit, big_endian) if raw else (img, printit)
-    finally:
-        if removefits:
-            os.remove(fitspath)
+            img = fitsio.read(origfitspath)
+            h = fitsio.read_header(origfitspath)
+    if not big_endian and img.dtype != _np.float32:
+        img = img.astype(_np.float32)
+    printit = _results_prefix(run, camcol, filter, field, h)
+    return (img, printit, big_endian) if raw else (img, printit)
 
 
 def _error_text(run, camcol, filter, field, exc):
@@ -127,7 +133,7 @@ NATIVE_INGEST = os.environ.get("LFD_NATIVE_INGEST", "1") != "0"
 
 
 class _RawHeader:
-    """The nine header cards of the results line as returned by lfd_fits_load_frame, parsed on access like a
+    """The nine header cards of the results line as returned by the native ingest, parsed on access like a
     FITSHeader (fitsio_lite._parse_value: same value formatting in the results line)."""
 
     def __init__(self, raw):
@@ -138,233 +144,290 @@ class _RawHeader:
         return _parse_value(self._raw[key])
 
 
+class _NativePrefix:
+    """Results-line prefix of a natively ingested frame, formatted only if the frame turns out to be a detection."""
+    __slots__ = ("frame", "ing", "j")
+
+    def __init__(self, frame, ing, j):
+        self.frame, self.ing, self.j = frame, ing, j
+
+    def __str__(self):
+        return _results_prefix(*self.frame, _RawHeader(self.ing.header(self.j)))
+
+
+def _stage(slot, img, big_endian):
+    """Put a frame into a pinned staging slot (viewed as uint32) as raw big-endian float32 payload."""
+    if big_endian:
+        slot[...] = img
+    else:
+        slot[...] = _np.ascontiguousarray(img, _np.float32).astype(">f4").view(_np.uint32)
+
+
 def _load_one(frame, params_removestars, slot=None, want_rects=True):
-    """Host side of one frame (runs in a loader thread): FITS image + header line prefix, photoObj catalog -> blot
-    rectangles.  With ``slot`` (a row of a handle's pinned staging viewed as uint32) an uncompressed frame of that
-    shape is read straight into it as raw big-endian payload.  With ``want_rects=False`` the catalog columns are
-    returned in place of the rectangles (the driver resolves a whole batch at once, star_rects_batch).
+    """Host side of one frame through the general (Python) readers - compressed frames, other layouts, anything the
+    native batch ingest declined: FITS image + header line prefix, photoObj catalog -> blot rectangles.  With ``slot``
+    (a row of a handle's pinned staging viewed as uint32) a frame of that shape is left there as raw big-endian payload.
     Returns ("staged", None, True, rects, printit) | ("ok", pixels, big_endian, rects, printit) | ("err", exc)."""
     run, camcol, filter, field = frame
     try:
-        staged = False
-        if slot is not None and hasattr(fitsio, "read_raw_image_into"):
-            path = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
-            if os.path.exists(path):
-                raw = _lib.fits_load_frame(path, slot) if NATIVE_INGEST else None      # native reader, GIL released
-                if raw is not None:
-                    h = _RawHeader(raw)
-                    printit = _results_prefix(run, camcol, filter, field, h)
-                    staged = True
-                else:
-                    try:
-                        h = fitsio.read_raw_image_into(path, slot)
-                        printit = _results_prefix(run, camcol, filter, field, h)
-                        staged = True
-                    except ValueError:
-                        staged = False
-        if not staged:
-            img, printit, big_endian = _load_frame(run, camcol, filter, field, raw=True)
-        shape = slot.shape if staged else img.shape
+        img, printit, big_endian = _load_frame(run, camcol, filter, field, raw=True)
         opath = files.filename("photoObj", run=run, camcol=camcol, field=field)
-        rects = _lib.catalog_rects(opath, filter, shape, **dict(params_removestars)) if NATIVE_INGEST else None
+        rects = _lib.catalog_rects(opath, filter, img.shape, **dict(params_removestars)) if NATIVE_INGEST else None
         if rects is None:                                    # not the plain table layout, or a value the reference raises on
             cat = read_photoObj_arrays(opath)
-            rects = star_rects(cat, filter, shape, **dict(params_removestars)) if want_rects else cat
-        if staged:
+            rects = star_rects(cat, filter, img.shape, **dict(params_removestars))
+        if slot is not None and tuple(img.shape) == tuple(slot.shape):
+            _stage(slot, img, big_endian)
             return ("staged", None, True, rects, printit)
         return ("ok", img, big_endian, rects, printit)
     except Exception as e:   # noqa: BLE001 - the reference swallows everything per frame
         return ("err", e)
 
 
-def _resolve_rects(loaded, chunk, shape0, params_removestars):
-    """Replace the catalog columns the loaders returned by blot rectangles: one vectorised call for the frames of
-    the batch that share the common frame shape, frame by frame for the others."""
-    loaded = list(loaded)
-    pr = dict(params_removestars)
-    def have(it):                                            # rectangles already resolved by the native ingest
-        return it[0] != "err" and isinstance(it[3], _np.ndarray)
-
-    group = [j for j, it in enumerate(loaded) if not have(it) and
-             (it[0] == "staged" or (it[0] == "ok" and it[1].shape == shape0))]
-    if group:
-        res = star_rects_batch([loaded[j][3] for j in group], [chunk[j][2] for j in group], shape0, **pr)
-        for j, r in zip(group, res):
-            loaded[j] = ("err", r) if isinstance(r, BaseException) else loaded[j][:3] + (r,) + loaded[j][4:]
-    for j, it in enumerate(loaded):
-        if it[0] == "ok" and j not in group and not have(it):
-            try:
-                loaded[j] = it[:3] + (star_rects(it[3], chunk[j][2], it[1].shape, **pr),) + it[4:]
-            except Exception as e:   # noqa: BLE001
-                loaded[j] = ("err", e)
-    return loaded
-
-
 _handles = {}
 N_RING = 3      # handles per frame shape: one computing, one submitted (crossing PCIe), one being filled by the loaders
 
 
+def _handle_caps():
+    """Optional capacities of the ring handles (tests shrink them to exercise the overflow retry)."""
+    return (int(os.environ.get("LFD_MAX_RUNS", 0)), int(os.environ.get("LFD_MAX_COMPONENTS", 0)))
+
+
 def _batch_handles(shape, batch, device, count=N_RING):
-    key = (shape, device)
+    key = (shape, device, _handle_caps())
     hs = _handles.get(key)
     if hs is None or hs[0].B < batch or len(hs) < count:
         for h in hs or []:
             h.close()
-        hs = [_lib.Handle(shape[0], shape[1], max_batch=batch, device=device) for _ in range(count)]
+        mr, mc = _handle_caps()
+        hs = [_lib.Handle(shape[0], shape[1], max_batch=batch, device=device, max_runs=mr, max_components=mc) for _ in range(count)]
         _handles[key] = hs
     return hs
 
 
-def _probe_shape(frames):
-    """Shape of the first readable frame (SDSS frames of a run all have one shape); None if none can be read."""
-    for (run, camcol, filter, field) in frames[:8]:
+def _big_handle(shape, device):
+    """One-frame handle with worst-case run / contour capacities: a frame that overflowed the batch handles' work lists
+    is run again here, so it gets the result the reference gives instead of an errors.txt entry."""
+    key = (shape, device, "worst-case")
+    h = _handles.get(key)
+    if h is None:
+        worst = shape[0] * ((shape[1] + 1) // 2)
+        h = _handles[key] = [_lib.Handle(shape[0], shape[1], max_batch=1, device=device, max_runs=worst, max_components=worst)]
+    return h[0]
+
+
+def _probe_shape(frames, params_removestars):
+    """Shape of the first frame that can be read (SDSS frames of a run all have one shape), compressed ones included;
+    None if none of the first few can be read."""
+    for fr in frames[:8]:
         try:
+            run, camcol, filter, field = fr
             path = files.filename("frame", run=run, camcol=camcol, field=field, filter=filter)
             if os.path.exists(path):
                 h = fitsio.read_header(path)
                 return (int(h["NAXIS2"]), int(h["NAXIS1"]))
+            img, _p, _b = _load_frame(run, camcol, filter, field, raw=True)
+            return tuple(int(v) for v in img.shape)
         except Exception:   # noqa: BLE001
             continue
     return None
 
 
-def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0, loaders=None):
-    """Run an ordered list of (run, camcol, filter, field) through the GPU in batches.  Returns one record per
-    frame, in list order: ("line", results_line) for a detection, ("none", "") for no detection,
-    ("err", errors_text) for a failure - exactly what the reference's per-frame loop would append.
+def _decode_batch(h, shape, n):
+    """lfd_wait + the verdict of every frame of the batch: [("ok", detected, result dict | None) | ("err", exc) |
+    ("overflow",)].  Only frames with a rectangle detection or a status bit go through the per-frame decoder."""
+    arr = h.wait_array()
+    out = [("ok", False, None)] * n
+    busy = _np.nonzero((arr["status"] != 0) | (arr["rect_detection"] == 1).any(axis=1))[0]
+    for k in busy:
+        k = int(k)
+        r = h._results[k]
+        if r.status & _lib.FRAME_OVERFLOW:
+            out[k] = ("overflow",)
+            continue
+        try:
+            det, res = False, None
+            for p in (0, 1):
+                if r.rect_detection[p] >= 0:
+                    det, res = result_from_device(r, p, shape)
+                    if det:
+                        break
+            out[k] = ("ok", det, res)
+        except Exception as e:   # noqa: BLE001
+            out[k] = ("err", e)
+    return out
 
-    Pipeline (three handles of the common frame shape form a ring): while batch k-1 computes and batch k crosses
-    PCIe, loader threads read the FITS payloads of batch k+1 straight into the third handle's pinned staging
-    (raw big-endian bytes, `readinto`, no GIL; the first kernel byte-swaps) and filter the catalogs.  Frames that
-    are compressed, of another shape or another BITPIX take the decoded-array path through the same ring."""
+
+def compute_fields_iter(frames, params_bright, params_dim, params_removestars, batch=16, device=0, loaders=None):
+    """Run an ordered list of (run, camcol, filter, field) through the GPU in batches.  Generator: yields, batch by batch
+    and in list order, ``(index of the batch's first frame, records)`` with one record per frame - ("line", results_line)
+    for a detection, ("none", "") for no detection, ("err", errors_text) for a failure - exactly what the reference's
+    per-frame loop would append.
+
+    Pipeline (three handles of the common frame shape form a ring): while batch k-1 computes and batch k crosses PCIe,
+    ONE native call (lfd_ingest_batch, a pool of C++ threads, GIL released) reads the raw big-endian FITS payloads of
+    batch k+1 straight into the third handle's pinned staging and filters its photoObj catalogs; the first kernel
+    byte-swaps.  Frames the native reader declines (compressed, scaled, another BITPIX) go through the Python readers on
+    loader threads (bz2 releases the GIL) and end up in the same staging slots; frames of another shape use a cached
+    handle of their own.  A frame whose run / contour lists overflow the batch handles is re-run on a worst-case-capacity
+    handle instead of being reported as an error."""
     from concurrent.futures import ThreadPoolExecutor
-    debug = bool(params_bright["debug"] or params_dim["debug"])
     frames = list(frames)
+    debug = bool(params_bright["debug"] or params_dim["debug"])
     if debug:
-        return _compute_fields_debug(frames, params_bright, params_dim, params_removestars)
+        recs = _compute_fields_debug(frames, params_bright, params_dim, params_removestars)
+        for i0 in range(0, len(frames), max(int(batch), 1)):
+            yield i0, recs[i0:i0 + max(int(batch), 1)]
+        return
     batch = max(int(batch), 1)
     chunks = [frames[i:i + batch] for i in range(0, len(frames), batch)]
-    records = [None] * len(frames)
-    outcome = {}             # global frame index -> ("ok", detected, result dict) | ("err", exc)
-    loaded_all = {}          # global frame index -> loader result
-    pending = []             # in-flight device batches: (handle, shape, [global indices])
-    shape0 = _probe_shape(frames)
+    pr = dict(params_removestars)
+    shape0 = _probe_shape(frames, pr)
     ring = []
     if shape0 is not None:
         try:
             ring = _batch_handles(shape0, batch, device)
         except Exception:   # noqa: BLE001 - reported per frame below, when the submit fails the same way
             ring = []
+    nload = (loaders or int(os.environ.get("LFD_LOADER_THREADS", 0)) or max(2, min(12, (os.cpu_count() or 2))))
 
-    def collect(entry):
-        h, shape, gidx = entry
-        try:
-            res = h.wait()
-        except Exception as e:   # noqa: BLE001
-            for g in gidx:
-                outcome[g] = ("err", e)
-            return
-        for k, g in enumerate(gidx):
+    def load_chunk(ci, fpool):
+        """Loader job of one batch (worker thread): native ingest of the whole batch, Python readers for the rest."""
+        chunk = chunks[ci]
+        h = ring[ci % len(ring)] if ring else None
+        st = h.host_frames.view(_np.uint32) if h is not None else None
+        items = [None] * len(chunk)
+        ing = None
+        if h is not None and NATIVE_INGEST:
             try:
-                r = res[k]
-                if r.status & _lib.FRAME_OVERFLOW:
-                    raise _lib.LfdError(_lib.LFD_E_CAPACITY, "per-frame work list overflow")
-                det, out = (False, None)
-                for p in (0, 1):
-                    if r.rect_detection[p] >= 0:
-                        det, out = result_from_device(r, p, shape)
-                        if det:
-                            break
-                outcome[g] = ("ok", det, out)
-            except Exception as e:   # noqa: BLE001
-                outcome[g] = ("err", e)
+                fpaths = [files.filename("frame", run=r, camcol=c, field=fd, filter=fl) for (r, c, fl, fd) in chunk]
+                cpaths = [files.filename("photoObj", run=r, camcol=c, field=fd) for (r, c, fl, fd) in chunk]
+                ing = _lib.ingest_batch(st, fpaths, cpaths, [fr[2] for fr in chunk], nthreads=nload, **pr)
+            except Exception:   # noqa: BLE001 - e.g. a filter that is not one of ugriz: the per-frame path raises it properly
+                ing = None
+        rest = []
+        for j, fr in enumerate(chunk):
+            if ing is not None and ing.status_frame[j] == 0 and ing.status_cat[j] == 0:
+                items[j] = ("staged", None, True, ing.rects[j, :ing.n_rects[j]], _NativePrefix(fr, ing, j))
+            else:
+                rest.append(j)
+        if rest:
+            for j, it in zip(rest, fpool.map(lambda jj: _load_one(chunk[jj], pr, st[jj] if st is not None else None), rest)):
+                items[j] = it
+        return items
 
-    def release(h):
-        for entry in [e for e in pending if e[0] is h]:
-            collect(entry)
-            pending.remove(entry)
+    def finish(entry):
+        """Collect one submitted batch -> {global index: ("ok", det, res) | ("err", exc)}."""
+        if entry[0] == "failed":
+            return {g: ("err", entry[2]) for g in entry[1]}
+        _tag, h, shape, gidx, rects, big_endian = entry
+        try:
+            dec = _decode_batch(h, shape, len(gidx))
+        except Exception as e:   # noqa: BLE001
+            return {g: ("err", e) for g in gidx}
+        out = {}
+        for k, g in enumerate(gidx):
+            d = dec[k]
+            if d[0] == "overflow":
+                try:
+                    big = _big_handle(shape, device)
+                    big.set_params(params_bright, params_dim)
+                    if big_endian:
+                        big.host_frames.view(_np.uint32)[0] = h.host_frames.view(_np.uint32)[k]
+                    else:
+                        big.host_frames[0] = h.host_frames[k]
+                    big.submit(1, [rects[k]], flags=_lib.INPUT_BIGENDIAN if big_endian else 0)
+                    d = _decode_batch(big, shape, 1)[0]
+                    if d[0] == "overflow":
+                        d = ("err", _lib.LfdError(_lib.LFD_E_CAPACITY, "per-frame work list overflow"))
+                except Exception as e:   # noqa: BLE001
+                    d = ("err", e)
+            out[g] = d
+        return out
 
     def submit(h, shape, gidx, rects, big_endian):
         try:
             h.set_params(params_bright, params_dim)
             h.submit(len(gidx), rects, flags=_lib.INPUT_BIGENDIAN if big_endian else 0)
-            pending.append((h, shape, gidx))
+            return ("entry", h, shape, gidx, rects, big_endian)
         except Exception as e:   # noqa: BLE001
-            for g in gidx:
-                outcome[g] = ("err", e)
+            return ("failed", gidx, e)
 
-    # measured on the 16-core host: 12 threads with the native ingest (3.2 k frames/s; 8: 2.7 k, 16: 2.8 k), 8 with the
-    # Python readers, which hold the GIL for longer (2.3 k; more threads only contend for it)
-    nload = (loaders or int(os.environ.get("LFD_LOADER_THREADS", 0)) or
-             max(2, min(12 if NATIVE_INGEST else 8, (os.cpu_count() or 2))))
-    with ThreadPoolExecutor(max_workers=nload) as pool:
-        futs = {}
-
-        def prefetch(ci):
-            if ci >= len(chunks) or ci in futs:
-                return
-            h = ring[ci % len(ring)] if ring else None
-            if h is not None:
-                release(h)                                   # its previous batch (ci - N_RING) is long done
-                st = h.host_frames.view(_np.uint32)
-                futs[ci] = [pool.submit(_load_one, fr, params_removestars, st[j], False) for j, fr in enumerate(chunks[ci])]
+    def records_of(ci, items, outcome):
+        recs = []
+        base = ci * batch
+        for j, (run, camcol, filter, field) in enumerate(chunks[ci]):
+            item, oc = items[j], outcome.get(base + j)
+            exc = item[1] if item[0] == "err" else (oc[1] if oc is not None and oc[0] == "err" else None)
+            if exc is None and oc is None:
+                exc = _lib.LfdError(_lib.LFD_E_STATE, "frame was not processed")
+            if exc is not None:
+                recs.append(("err", _error_text(run, camcol, filter, field, exc)))
+            elif oc[1]:
+                res = oc[2]
+                recs.append(("line", str(item[4]) + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n"))
             else:
-                futs[ci] = [pool.submit(_load_one, fr, params_removestars, None, False) for fr in chunks[ci]]
+                recs.append(("none", ""))
+        return recs
 
-        prefetch(0)
+    with ThreadPoolExecutor(max_workers=2) as bpool, ThreadPoolExecutor(max_workers=nload) as fpool:
+        futs = {0: bpool.submit(load_chunk, 0, fpool)} if chunks else {}
+        inflight = []            # [(ci, items, submitted entries, {outcomes known so far})] in submission order
+
+        def drain(upto):
+            """Collect (and yield the records of) every submitted batch with index <= upto, oldest first."""
+            while inflight and inflight[0][0] <= upto:
+                cj, itj, ents, oc = inflight.pop(0)
+                for e in ents:
+                    oc.update(finish(e))
+                yield cj * batch, records_of(cj, itj, oc)
+
         for ci, chunk in enumerate(chunks):
-            prefetch(ci + 1)
-            loaded = _resolve_rects([f.result() for f in futs.pop(ci)], chunk, shape0, params_removestars)
+            # the handle batch ci+1 loads into is the one batch ci-2 used (ring of three): collect that one, then start
+            # the next load so that it runs while batch ci is submitted and batch ci-1 computes
+            yield from drain(ci - (len(ring) - 1 if ring else 1))
+            if ci + 1 < len(chunks):
+                futs[ci + 1] = bpool.submit(load_chunk, ci + 1, fpool)
+            items = futs.pop(ci).result()
             base = ci * batch
-            for j, item in enumerate(loaded):
-                loaded_all[base + j] = item
             h = ring[ci % len(ring)] if ring else None
-            staged = [j for j, it in enumerate(loaded) if it[0] == "staged"]
-            others = {}
-            for j, it in enumerate(loaded):
-                if it[0] == "ok":
-                    others.setdefault((it[1].shape, it[2]), []).append(j)
+            outcome = {}
+            entries = []
+            staged = [j for j, it in enumerate(items) if it[0] == "staged"]
             if staged:
-                # staged frames sit in their own slots; compact them to the front (a frame that failed or took the
-                # other path leaves a hole)
+                # staged frames sit in their own slots; compact them to the front (a frame that failed or took
+                # another path leaves a hole)
                 st = h.host_frames.view(_np.uint32)
                 for k, j in enumerate(staged):
                     if k != j:
                         st[k] = st[j]
-                submit(h, shape0, [base + j for j in staged], [loaded[j][3] for j in staged], True)
+                entries.append(submit(h, shape0, [base + j for j in staged], [items[j][3] for j in staged], True))
+            others = {}
+            for j, it in enumerate(items):
+                if it[0] == "ok":
+                    others.setdefault((tuple(it[1].shape), bool(it[2])), []).append(j)
             for (shape, big_endian), idxs in others.items():
+                # another frame shape (or no ring): a cached handle of that shape, run to completion right away
                 gidx = [base + j for j in idxs]
                 try:
-                    if h is not None and shape == shape0 and not staged:
-                        hh = h
-                    else:
-                        # rare: another frame shape, or a second group in this chunk -> a handle of its own, synchronously
-                        hh = _lib.Handle(shape[0], shape[1], max_batch=len(idxs), device=device)
+                    hh = _batch_handles(shape, batch, device, count=1)[0]
                     stg = hh.host_frames.view(_np.uint32) if big_endian else hh.host_frames
                     for slot, j in enumerate(idxs):
-                        stg[slot] = loaded[j][1]
-                    submit(hh, shape, gidx, [loaded[j][3] for j in idxs], big_endian)
-                    if hh is not h:
-                        release(hh)
-                        hh.close()
+                        stg[slot] = items[j][1]
+                    outcome.update(finish(submit(hh, shape, gidx, [items[j][3] for j in idxs], big_endian)))
                 except Exception as e:   # noqa: BLE001
-                    for g in gidx:
-                        outcome[g] = ("err", e)
-        for entry in list(pending):
-            collect(entry)
-    for g, (run, camcol, filter, field) in enumerate(frames):
-        item = loaded_all[g]
-        exc = item[1] if item[0] == "err" else (outcome[g][1] if outcome[g][0] == "err" else None)
-        if exc is not None:
-            if debug:
-                traceback.print_exception(type(exc), exc, exc.__traceback__, limit=3)
-            records[g] = ("err", _error_text(run, camcol, filter, field, exc))
-        elif outcome[g][1]:
-            res = outcome[g][2]
-            records[g] = ("line", item[4] + f"{res['x1']} {res['y1']} {res['x2']} {res['y2']}\n")
-        else:
-            records[g] = ("none", "")
-    return records
+                    outcome.update({g: ("err", e) for g in gidx})
+            inflight.append((ci, items, entries, outcome))
+        yield from drain(len(chunks))
+
+
+def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0, loaders=None):
+    """All records of ``compute_fields_iter`` as one list in frame order."""
+    out = []
+    for _i0, recs in compute_fields_iter(frames, params_bright, params_dim, params_removestars, batch=batch, device=device,
+                                         loaders=loaders):
+        out.extend(recs)
+    return out
 
 
 def _compute_fields_debug(frames, params_bright, params_dim, params_removestars):
@@ -419,43 +482,54 @@ def read_progress(path):
 def process_fields(results, errors, frames, params_bright, params_dim, params_removestars, batch=16, device=0,
                    distributed=None, compute=None, progress=None):
     """Process an ordered list of (run, camcol, filter, field); results/errors are written in list order,
-    exactly the lines the reference's per-frame loop would write.
+    exactly the lines the reference's per-frame loop would write, and flushed after every GPU batch (the reference
+    appends frame by frame, detecttrails.py:127-139: a killed run keeps what it finished).
 
     With ``torch.distributed`` initialised (one process per GPU, e.g. under torchrun) the list is sharded by
     frame across the ranks - blocks of ``batch`` consecutive frames dealt round-robin, no data-path collective -
     and rank 0 gathers the per-frame records and writes them in the original order (lfd_b200/sharding.py).
     ``distributed=False`` forces the single-process path; ``compute`` replaces the GPU stage (tests)."""
     from . import sharding
-    compute = compute or (lambda fr: compute_fields(fr, params_bright, params_dim, params_removestars, batch=batch, device=device))
     frames = list(frames)
     if distributed is None:
         distributed = sharding.is_distributed()
     # resumable runs (SURVEY.md 8(f) N3): `progress` is a text file with one line per finished frame; frames listed
-    # there are skipped, and the file is extended chunk by chunk, after the chunk's results/errors lines are flushed
+    # there are skipped, and the file is extended batch by batch, right after the batch's results/errors lines are flushed
     if progress:
         done = read_progress(progress)
         frames = [fr for fr in frames if _progress_key(fr) not in done]
     writer = (not distributed) or sharding.rank() == 0
-    # frames per compute call: the ring drains and refills at every call boundary (one un-overlapped batch load plus
-    # one un-overlapped batch of compute, ~15 ms), so calls are long; a progress file is extended once per call
-    chunk = max(batch, 1) * (sharding.world_size() if distributed else 1) * 32
+
+    def emit(part, recs):
+        write_records(results, errors, recs)
+        results.flush(); errors.flush()
+        if progress:
+            with open(progress, "a") as pf:
+                pf.write("".join(_progress_key(fr) + " " + kind + "\n" for fr, (kind, _text) in zip(part, recs)))
+
+    if not distributed:
+        if compute is not None:                       # injected compute stage (tests): one call per `batch * 32` frames
+            step = max(batch, 1) * 32
+            for i0 in range(0, len(frames), step):
+                emit(frames[i0:i0 + step], compute(frames[i0:i0 + step]))
+            return
+        for i0, recs in compute_fields_iter(frames, params_bright, params_dim, params_removestars, batch=batch, device=device):
+            emit(frames[i0:i0 + len(recs)], recs)
+        return
+    compute = compute or (lambda fr: compute_fields(fr, params_bright, params_dim, params_removestars, batch=batch, device=device))
+    # frames per gather: every rank runs `32` of its own batches between two gathers (the ring drains at a gather)
+    chunk = max(batch, 1) * sharding.world_size() * 32
     for i0 in range(0, len(frames), chunk):
         part = frames[i0:i0 + chunk]
-        recs = sharding.run_sharded(part, compute, block=batch) if distributed else compute(part)
-        if not writer:
-            continue
-        write_records(results, errors, recs)
-        if progress:
-            results.flush(); errors.flush()
-            with open(progress, "a") as pf:
-                for fr, (kind, _text) in zip(part, recs):
-                    pf.write(_progress_key(fr) + " " + kind + "\n")
+        recs = sharding.run_sharded(part, compute, block=batch)
+        if writer:
+            emit(part, recs)
 
 
 def process_field(results, errors, run, camcol, filter, field, params_bright, params_dim, params_removestars):
-    """detecttrails.py:30-143 for one frame."""
+    """detecttrails.py:30-143 for one frame (always in this process: a single frame is never sharded)."""
     process_fields(results, errors, [(run, camcol, filter, field)], params_bright, params_dim,
-                   params_removestars, batch=1)
+                   params_removestars, batch=1, distributed=False)
 
 
 class DetectTrails:

@@ -13,6 +13,7 @@ This module covers exactly those three calls for the two file kinds on the path:
 ``read_raw_image`` additionally returns the *undecoded* big-endian payload so the frame
 driver can upload it and byte-swap on the device.
 """
+import io
 import os
 import re
 
@@ -202,7 +203,10 @@ def _native(arr):
 
 def _iter_hdus_f(f):
     """(header, data offset, data bytes) of every HDU of the open file ``f``; the caller may seek between items."""
-    size = os.fstat(f.fileno()).st_size
+    try:
+        size = os.fstat(f.fileno()).st_size
+    except (AttributeError, OSError, io.UnsupportedOperation):      # an in-memory file (io.BytesIO)
+        size = f.seek(0, 2)
     pos = 0
     while pos < size:
         f.seek(pos)
@@ -329,6 +333,28 @@ def read_raw_image(path):
         arr = np.frombuffer(buf, dtype=np.uint32).reshape(h["NAXIS2"], h["NAXIS1"])
         return arr, h
     raise OSError("no image HDU in %s" % path)
+
+
+def read_image_bytes(buf):
+    """The primary image of a FITS file held in memory (``bytes``, e.g. a decompressed ``.fits.bz2``): returns
+    ``(pixels, header, big_endian)`` - the undecoded big-endian payload as a uint32 array when the image is a plain
+    unscaled BITPIX=-32 one (big_endian True: the device byte-swaps), else the decoded native array like ``read``."""
+    f = io.BytesIO(buf)
+    for h, pos, nbytes in _iter_hdus_f(f):
+        if nbytes == 0:
+            continue
+        try:
+            if h["BITPIX"] != -32 or h["NAXIS"] != 2:
+                raise ValueError("not a 2-D BITPIX=-32 image")
+            _require_unscaled(h)
+            n = 4 * h["NAXIS1"] * h["NAXIS2"]
+            if pos + n > len(buf):
+                raise OSError("truncated FITS data")
+            arr = np.frombuffer(buf, dtype=np.uint32, count=n // 4, offset=pos).reshape(h["NAXIS2"], h["NAXIS1"])
+            return arr, h, True
+        except ValueError:
+            return _read_hdu(None, h, pos, nbytes, f), h, False
+    raise OSError("No extensions have data")
 
 
 def read_raw_image_into(path, dest):

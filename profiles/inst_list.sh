@@ -34,5 +34,11 @@ with open("$OUT/inst_${TAG}_summary.txt", "w") as f:
         f.write("%-28s %8.1f %10.2f %8.1f %8.1f %8.1f %9.1f\n" % (name, n / nsteps, p["smsp__inst_executed.sum"] / nsteps / 1e6, 100 * p["smsp__inst_executed.sum"] / tot_i,
                 p["gpu__time_duration.sum"] / nsteps / 1e3, p["smsp__issue_active.avg.pct_of_peak_sustained_active"] / n,
                 100 * p["sm__cycles_active.avg"] / max(p["sm__cycles_elapsed.max"], 1)))
+import json
+json.dump({"batch": 64, "workload": "config3", "steps_captured": nsteps, "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum (profiles/inst_list.sh $TAG)",
+           "unit": "bytes per 64-frame step, both passes, all launches of the kernel",
+           "per_step_bytes": {name: (p["dram__bytes_read.sum"] + p["dram__bytes_write.sum"]) / nsteps for name, p in per.items()},
+           "per_step_minst": {name: p["smsp__inst_executed.sum"] / nsteps / 1e6 for name, p in per.items()}},
+          open("$OUT/traffic_$TAG.json", "w"), indent=1)
 PY
 cat $OUT/inst_${TAG}_summary.txt

@@ -133,3 +133,48 @@ def test_dropin_batches_match_oracle(tmp_path, cv2mod):
     assert got == "".join(exp)
     assert len(exp) >= 10
     assert (out / "errors.txt").read_text() == ""
+
+
+def test_dropin_bz2_frames_and_overflow_retry(tmp_path, cv2mod, monkeypatch):
+    """Compressed frames (detecttrails.py:81-111: `<frame>.fits.bz2` when the plain file is absent) go through the
+    loader threads and the same staging slots as plain ones; a frame whose run / contour lists overflow the batch
+    handles' capacities is re-run on a worst-case handle - either way results.txt is what the oracle derives and
+    errors.txt stays empty."""
+    import bz2
+    import lfd_b200
+    import lfd_b200.detecttrails as dtm
+    from lfd_b200 import fitsio_lite
+    fields = list(range(300, 312))
+    names = ["trail_var", "dense_heavy", "sparse", "satellite", "dense", "trail", "sparse", "dense_trail", "faint_trail", "sparse",
+             "trail_axis", "dense_heavy"]
+    kinds = {("i", f): k for f, k in zip(fields, names)}
+    tree = synth.write_sdss_tree(str(tmp_path), 2888, 4, fields, filters=("i",), kinds=kinds, startfield=300, endfield=312)
+    fdir = os.path.join(tree["photoobjpath"], "frames", "301", "2888", "4")
+    hdrs = {}
+    for f in fields:
+        path = os.path.join(fdir, "frame-i-002888-4-%04d.fits" % f)
+        hdrs[f] = fitsio_lite.read_header(path)
+        if f % 2 == 0:                                            # every other frame exists only compressed
+            with open(path, "rb") as src, open(path + ".bz2", "wb") as dst:
+                dst.write(bz2.compress(src.read(), 1))
+            os.remove(path)
+    lfd_b200.setup(tree["bosspath"], tree["photoobjpath"], tree["photoreduxpath"], str(tmp_path))
+    ref = verdicts([tree["frames"][("i", f)][0] for f in fields], [tree["frames"][("i", f)][1] for f in fields], ["i"] * len(fields))
+    exp = "".join(rp.result_line(2888, 4, "i", f, hdrs[f], v[2]) for f, v in zip(fields, ref) if v[0] is True)
+    assert exp.count("\n") >= 4
+
+    def run(tag):
+        out = tmp_path / tag
+        out.mkdir()
+        lfd_b200.DetectTrails(run=2888, camcol=4, filter="i", savepath=str(out), batch=5).process()
+        return (out / "results.txt").read_text(), (out / "errors.txt").read_text()
+
+    assert run("plain") == (exp, "")
+    # tiny work-list capacities: the dense fields overflow in the batch handles and are retried one by one
+    monkeypatch.setenv("LFD_MAX_RUNS", "6000")
+    monkeypatch.setenv("LFD_MAX_COMPONENTS", "600")
+    calls = []
+    real = dtm._big_handle
+    monkeypatch.setattr(dtm, "_big_handle", lambda shape, device: (calls.append(shape), real(shape, device))[1])
+    assert run("tiny") == (exp, "")
+    assert len(calls) >= 2, "no frame overflowed: the retry path was not exercised"

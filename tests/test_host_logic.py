@@ -256,14 +256,32 @@ def test_native_ingest_equals_python(tmp_path):
     assert _lib.catalog_rects(q, "r", (H, W), **rp.DEFAULT_REMOVESTARS) is None
     # the loader takes the native path by default and the Python path on request: same record either way
     fr = (2888, 1, "g", 101)
-    a = dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_n, False)
+    a = dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_n)
     old = dtm.NATIVE_INGEST
     try:
         dtm.NATIVE_INGEST = False
-        b = dtm._resolve_rects([dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_p, False)], [fr], (H, W), rp.DEFAULT_REMOVESTARS)[0]
+        b = dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_p)
     finally:
         dtm.NATIVE_INGEST = old
     assert a[0] == b[0] == "staged" and np.array_equal(a[3], b[3]) and a[4] == b[4] and np.array_equal(slot_n, slot_p)
+    # the batched native ingest (one call, a pool of C++ threads) == the per-frame readers, item by item; a missing
+    # catalog or frame only fails its own item
+    frames = [(2888, 1, flt, field) for field in (100, 101, 102) for flt in "ugriz"]
+    fpaths = [sdssfiles.filename("frame", run=r, camcol=c, field=fd, filter=fl) for (r, c, fl, fd) in frames]
+    cpaths = [sdssfiles.filename("photoObj", run=r, camcol=c, field=fd) for (r, c, fl, fd) in frames]
+    fpaths[4] = str(tmp_path / "missing-frame.fits")
+    cpaths[7] = str(tmp_path / "missing-cat.fits")
+    staging = np.zeros((len(frames), H, W), np.uint32)
+    ing = _lib.ingest_batch(staging, fpaths, cpaths, [fr[2] for fr in frames], nthreads=4, **rp.DEFAULT_REMOVESTARS)
+    assert ing is not None
+    for i, fr in enumerate(frames):
+        assert (ing.status_frame[i] == 0) == (i != 4) and (ing.status_cat[i] == 0) == (i != 7)
+        if i == 4 or i == 7:
+            continue
+        ref = dtm._load_one(fr, rp.DEFAULT_REMOVESTARS, slot_p)
+        assert ref[0] == "staged" and np.array_equal(staging[i], slot_p)
+        assert np.array_equal(ing.rects[i, :ing.n_rects[i]], ref[3])
+        assert str(dtm._NativePrefix(fr, ing, i)) == ref[4]
 
 
 def test_scaled_frames_take_the_decoded_path(tmp_path):
