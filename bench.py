@@ -212,7 +212,7 @@ def cpu_frames_per_s_files(frames, cats, nframes, cores):
     from lfd_b200 import fitsio_lite
     root = tempfile.mkdtemp(prefix="lfd_b200_cpu_")
     try:
-        nd = min(len(frames), 16)
+        nd = len(frames)                                  # the same frames, in the same order, as the compute-only leg
         for i in range(nd):
             fitsio_lite.write_image(os.path.join(root, "frame%d.fits" % i), frames[i], dict(synth.DEFAULT_HEADER))
             fitsio_lite.write_bintable(os.path.join(root, "photoObj%d.fits" % i), cats[i])
