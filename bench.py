@@ -173,11 +173,15 @@ class ClockSampler:
 _CPU_PARAMS = (None, None)      # (params_bright, params_dim) of the workload, inherited by the forked workers
 
 
-def _cpu_worker(args):
+_CPU_POOL = None                # (frames, cats): inherited by the forked workers, so a job is an index, not 12 MB of pickle
+
+
+def _cpu_worker(i):
     import cv2
     cv2.setNumThreads(1)
     from oracle import ref_pipeline as rp
-    img, cat, flt = args
+    frames, cats = _CPU_POOL
+    img, cat, flt = frames[i % len(frames)], cats[i % len(frames)], synth.FILTERS[i % 5]
     t = time.perf_counter()
     try:
         rp.process_frame(img.copy(), cat, flt, _CPU_PARAMS[0], _CPU_PARAMS[1])
@@ -229,16 +233,18 @@ def cpu_frames_per_s_files(frames, cats, nframes, cores):
 
 
 def cpu_frames_per_s(frames, cats, nframes, cores, repeat=1):
-    """Wall-clock frames/s of the oracle pipeline over `nframes` frames on `cores` processes."""
+    """Wall-clock frames/s of the oracle pipeline over `nframes` frames on `cores` processes (frames already decoded in
+    RAM and shared with the workers by fork, so no per-job transfer is timed)."""
+    global _CPU_POOL
     import multiprocessing as mp
-    jobs = [(frames[i % len(frames)], cats[i % len(frames)], synth.FILTERS[i % 5]) for i in range(nframes)]
+    _CPU_POOL = (frames, cats)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs[:cores])          # warm the workers (imports, page-in)
+        pool.map(_cpu_worker, range(cores))          # warm the workers (imports, page-in)
         best = None
         for _ in range(repeat):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker, jobs, chunksize=1)
+            pool.map(_cpu_worker, range(nframes), chunksize=1)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return nframes / best, best
@@ -258,13 +264,14 @@ def run_reference(args):
     cal_value, _ = cpu_frames_per_s(frames, cats, max(2 * cores, 8), cores)
     per_step = int(min(max(cal_value * 4.0, 2 * cores), 2048))   # ~4 s of all-core CPU work per step
     import multiprocessing as mp
-    jobs = [(frames[i % len(frames)], cats[i % len(frames)], synth.FILTERS[i % 5]) for i in range(per_step)]
+    global _CPU_POOL
+    _CPU_POOL = (frames, cats)
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(args.warmup, 1)):
-            pool.map(_cpu_worker, jobs[:cores])
+            pool.map(_cpu_worker, range(cores))
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_worker, jobs, chunksize=1)
+            pool.map(_cpu_worker, range(per_step), chunksize=1)
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     import cv2
@@ -452,29 +459,49 @@ def run_ours(args):
     # ---- value: batch resident in HBM -------------------------------------------------------
     res = hA.upload(B, rects)                          # H2D once (+ one untimed run)
     n_detect = sum(r.detected for r in res)
-    for _ in range(args.warmup):
-        hA.run_resident(B); hA.wait()
+    pipelined = not args.serial_steps
+    if pipelined:
+        hB.upload(B, rects)                            # the second handle holds the same resident batch
+    hs2 = (hA, hB)
+
+    def resident_loop(steps):
+        """K steps back to back.  Pipelined (default): two handles alternate with two steps in flight, so the memory-bound
+        head of step k+1 (setup + k_prep) overlaps the latency-bound tail of step k, exactly as consecutive batches do in the
+        e2e leg and in the drop-in driver.  --serial-steps: one handle, every step collected before the next is launched."""
+        last = [None, None]
+        prep = 0.0
+        if not pipelined:
+            for _ in range(steps):
+                hA.run_resident(B); last[0] = hA.wait()
+                prep += hA.timings()[1][1]
+            return last, prep, hA
+        hs2[0].run_resident(B)
+        for k in range(1, steps):
+            hs2[k & 1].run_resident(B)
+            last[(k - 1) & 1] = hs2[(k - 1) & 1].wait()
+            prep += hs2[(k - 1) & 1].timings()[1][1]
+        last[(steps - 1) & 1] = hs2[(steps - 1) & 1].wait()
+        prep += hs2[(steps - 1) & 1].timings()[1][1]
+        return last, prep, hs2[(steps - 1) & 1]
+
+    resident_loop(max(args.warmup, 3))
     sampler = ClockSampler(local)
     stage_ms = None
     barrier()
     sampler.start()
-    l0 = hA.kernel_launches()
+    l0 = hA.kernel_launches() + hB.kernel_launches()
     t0 = time.perf_counter()
-    prep_ms_sum = 0.0
     hA.timer_mark(0)
-    res_resident = None
-    for _ in range(args.steps):
-        hA.run_resident(B); res_resident = hA.wait()
-        prep_ms_sum += hA.timings()[1][1]             # k_prep runs before the passes fork: its bracket is clean
-    res_resident = [bytes(r) for r in res_resident]
-    hA.timer_mark(1)
-    dev_ms = hA.timer_elapsed_ms(0, hA, 1)            # CUDA events on the library's stream, first launch -> last result
+    last_res, prep_ms_sum, h_last = resident_loop(args.steps)   # k_prep runs before the passes fork: its bracket is clean
+    res_resident = [bytes(r) for r in (last_res[(args.steps - 1) & 1] if pipelined else last_res[0])]
+    h_last.timer_mark(1)
+    dev_ms = hA.timer_elapsed_ms(0, h_last, 1)        # CUDA events on the library's streams, first launch -> last result
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
     wall_s = time.perf_counter() - t0
     sampler.pause()
-    launches = hA.kernel_launches() - l0
+    launches = hA.kernel_launches() + hB.kernel_launches() - l0
     elapsed = reduce_max(dev_ms) / 1e3
     wall_s = reduce_max(wall_s)
     counters = hA.counters()
@@ -644,12 +671,22 @@ def run_ours(args):
     dom_bytes = sum(e["alg_bytes_per_step"] for e in dom_rows)
     dom_ms = sum(e["ms_per_step"] for e in dom_rows)
     dom_launches = sum(e["launches_per_step"] for e in dom_rows)
+    # the same kernel with nothing else on the GPU: its stage brackets of the serialised steps (one launch per pass over the
+    # whole batch) - what the kernel itself achieves, next to what it achieves while sharing the SMs with three other streams
+    alone = None
+    stage_of = {"k_nms_march": "sobel+nms", "k_morph_march": "lut+morph"}
+    if dom in stage_of:
+        ms_alone = sum(ms for n_, ms in stage_ms if n_.split(":")[-1].startswith(stage_of[dom]))
+        if ms_alone > 0:
+            alone = {"ms_per_step": ms_alone, "gbs": dom_bytes / (ms_alone * 1e6), "frac": dom_bytes / (ms_alone * 1e6) / peak,
+                     "how": "CUDA-event stage brackets of the %d steps run with LFD_SERIAL_PASSES (one stream, one launch per pass)" % n_serial}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e6), "peak": peak, "unit": "GB/s",
                 "frac": dom_bytes / (dom_ms * 1e6) / peak,
                 "traffic": (measured[dom] / dom_launches) if dom in measured else None,
                 "traffic_source": measured_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes / dom_launches, "avg_launch_ms": dom_ms / dom_launches,
                 "launches_per_step": dom_launches, "ms_per_step": dom_ms, "bracketed_ms_per_step": bracketed_ms_per_step,
+                "alone": alone,
                 "all_kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(tot_by_kernel.items(), key=lambda kv: -kv[1])},
                 "note": "time-dominant HBM-stage kernel (both passes, all batch parts). Durations are CUDA events recorded on the "
                         "launching stream around every launch inside the captured graph, over a second run of the same K steps "
@@ -705,7 +742,10 @@ def run_ours(args):
                    "(sparse/dense/trail/satellite mix, seeded), inputs %.0f MB per step > L2 (126 MB), no L2 flush" % (B * N * 4 / 1e6),
                    "kinds": {k: kinds.count(k) for k in sorted(set(kinds))}, "detections_per_batch": int(n_detect),
                    "parallelism": "frame-sharded x%d, no collective" % world, "host_cpus_bound_per_rank": numa},
-        "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside: "
+        "timing": ("resident leg: K steps issued back to back on two handles holding the same resident batch, two steps in flight "
+                   "(the head of step k+1 overlaps the tail of step k; --serial-steps measures one step at a time); " if pipelined else
+                   "resident leg: one handle, every step collected before the next is launched; ") +
+                  "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside: "
                   "%.3f ms/step resident, %.3f ms/step e2e" % (1e3 * wall_s / args.steps, 1e3 * e2e_wall / args.steps),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -923,6 +963,8 @@ def main():
                          "(15x15 dilation, fine rho), 5 = Hough/Canny microbench on 4096x4096")
     ap.add_argument("--hough-method", type=float, default=1.0, help="config4: params_dim['houghMethod'] (rho resolution, px)")
     ap.add_argument("--quick", action="store_true", help="config5: first four cases only")
+    ap.add_argument("--serial-steps", action="store_true",
+                    help="resident leg: collect every step before launching the next (default: two handles, two steps in flight)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (target command for ncu)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the DetectTrails-on-FITS-files leg")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed steps' results")

@@ -128,8 +128,12 @@ k_canny_nms(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
 // ================================================================================================
 #include "k_morph.cuh"
 
+#ifndef NMS_R
 #define NMS_R 32
+#endif
+#ifndef NMS_WPC
 #define NMS_WPC 1                // warps (= strip units) per CTA: units differ a lot in work (skips), so small CTAs free their slot sooner
+#endif
 
 __device__ __forceinline__ u32 vneg2(u32 a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ u32 vsub2(u32 a, u32 b) { return __vadd2(a, vneg2(b)); }

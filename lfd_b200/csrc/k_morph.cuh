@@ -164,10 +164,14 @@ k_morph(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict_
 // unrolled by lcm(EH, DH)), so the image is read once from global memory and nothing is staged in
 // shared memory except the 256-byte LUT.
 // ================================================================================================
+#ifndef MARCH_R
 #define MARCH_R 64            // output rows per warp
+#endif
 #define MARCH_UW 56           // useful words per strip (7 mask words)
 #define MARCH_HW 4            // halo words per side (lanes 0,1 and 30,31)
+#ifndef MARCH_WPC
 #define MARCH_WPC 1           // warps (= strip units) per CTA
+#endif
 
 template <bool IS_MAX> __device__ __forceinline__ u32 mm2(u32 a, u32 b) { return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b); }
 template <bool IS_MAX> __device__ __forceinline__ u32 mm3(u32 a, u32 b, u32 c)
