@@ -121,3 +121,26 @@ def test_hough_standalone(handle, cv2mod):
                 if ref is not None:
                     assert got.shape == ref.shape, (H, W, rho, theta, got.shape, ref.shape)
                     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (H, W, rho, theta)
+
+
+def test_hough_fine_rho_on_blobs(handle, cv2mod):
+    """Fine rho on blob-like full-size masks (what config 4 feeds HoughLines: rho = 1 px on the 15x15-dilated plane;
+    2-4 angles per CTA, words walked bit by bit, single privatised copy flushed with plain stores): the accumulator
+    equals the restated one cell for cell and the line list equals cv2.HoughLines bit for bit."""
+    rng = np.random.default_rng(11)
+    H, W = synth.FRAME_H, synth.FRAME_W
+    img = np.zeros((H, W), np.uint8)
+    for _ in range(140):                                        # filled boxes: mask words are mostly full (>= 6 px per word)
+        x, y = int(rng.integers(0, W - 90)), int(rng.integers(0, H - 60))
+        img[y:y + int(rng.integers(12, 60)), x:x + int(rng.integers(30, 90))] = int(rng.integers(1, 256))
+    cv2mod.line(img, (40, 30), (W - 60, H - 90), 255, 9)
+    words = img.reshape(H, W // 32, 32)
+    nzw = (words != 0).any(axis=2).sum()
+    assert np.count_nonzero(img) >= 6 * nzw, "test image is not blob-like (mask words should be mostly full)"
+    for rho in (1, 2, 0.5):
+        ref = cv2mod.HoughLines(img, rho, np.pi / 180, 1)
+        got, accum = handle.hough_lines(img, rho, np.pi / 180, 1, want_accum=True)
+        _, racc, _ = cr.hough_lines(img, rho, np.pi / 180, 1)
+        assert np.array_equal(accum, racc), rho
+        assert ref is not None and got is not None and got.shape == ref.shape, rho
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), rho
