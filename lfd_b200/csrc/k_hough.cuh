@@ -125,13 +125,17 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
 #define HOUGH_R(xx) hough_r<MAGIC>((xx), c, ys)
     // The segment list is read two iterations ahead: an iteration is a dependent chain behind one 8-byte load (L2
     // latency ~600 cycles against ~100 cycles of work), so without the prefetch the kernel waits on memory.
-    const int step = nwarps * per;
+    // When a warp covers `per` > 1 words at once (fine rho: few angles per CTA), those words are taken from `per` distant
+    // slices of the raster-ordered list (word si of slice `sub`), not from `per` neighbours: vertically adjacent words of
+    // a blob vote for the same bins at the same moment, and same-address shared-memory atomics serialise.
+    const int S = (nseg + per - 1) / per;              // words per slice
+    const int step = nwarps;
     auto fetch = [&](int si) -> uint2 {
-        const int idx = si + sub;
-        return (live && idx < nseg) ? __ldg(sg + idx) : make_uint2(0u, 0u);
+        const int idx = si + sub * S;
+        return (live && si < S && idx < nseg) ? __ldg(sg + idx) : make_uint2(0u, 0u);
     };
-    uint2 q0 = fetch(warp * per), q1 = fetch(warp * per + step);
-    for (int si = warp * per; si < nseg; si += step) {
+    uint2 q0 = fetch(warp), q1 = fetch(warp + step);
+    for (int si = warp; si < S; si += step) {
         const uint2 sgv = q0;
         q0 = q1;
         q1 = fetch(si + 2 * step);

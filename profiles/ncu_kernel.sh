@@ -4,7 +4,7 @@
 set -u
 TAG=$1; KRE=$2; SKIP=${3:-0}; CNT=${4:-4}
 OUT=gpurun_out
-CMD="python bench.py --profile --batch 64 --steps 2 --warmup 3"
+CMD="python bench.py --profile --batch 64 --steps 2 --warmup 3 ${BENCH_ARGS:-}"
 export LFD_NO_GRAPH=1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s $SKIP -c $CNT -o $OUT/prof_$TAG -f $CMD > $OUT/ncu_$TAG.log 2>&1
 echo "capture rc=$?"
