@@ -185,16 +185,24 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
                 HVOTE(r2, __popc(m & bit_range(hi2, lb)));
             }
         } else {
-            int cur = r1, cnt = 1;
+            // more than two bin boundaries inside the word (fine rho): the bins change at most pixels, so merging equal
+            // neighbours saved few atomics and cost a divergent branch per pixel (37 executed instructions per vote at
+            // rho = 1, ncu profiles/r02n_hough_c4_*); every pixel votes on its own, two independent evaluations per
+            // iteration to overlap their dependent FP32 chains
+            natom += __popc(m);
+            atomicAdd(&row[r1], 1);
             m &= m - 1;
             while (m) {
-                int b = __ffs(m) - 1;
+                const int b0 = __ffs(m) - 1;
                 m &= m - 1;
-                int r = HOUGH_R(x0 + b);
-                if (r == cur) cnt++;
-                else { HVOTE(cur, cnt); cur = r; cnt = 1; }
+                const int ra = HOUGH_R(x0 + b0);
+                if (m) {
+                    const int b1 = __ffs(m) - 1;
+                    m &= m - 1;
+                    atomicAdd(&row[HOUGH_R(x0 + b1)], 1);
+                }
+                atomicAdd(&row[ra], 1);
             }
-            HVOTE(cur, cnt);
         }
     }
 #undef HOUGH_R
