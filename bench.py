@@ -633,6 +633,10 @@ def run_ours(args):
     #   shared-memory accumulators): they carry measured DRAM bytes only, no roofline fraction.
     alg_frame = {("k_prep", 0): 6 * N, ("k_morph_march", 0): 4 * N, ("k_morph_march", 1): (6 if has_erode else 4) * N,
                  ("k_nms_march", 0): 2 * N, ("k_nms_march", 1): 2 * N}
+    # what THIS design has to move per frame for the same stages (the LUT is applied inside the morphology kernel, erode and
+    # dilate share one pass over the plane, NMS writes two 1-bit masks): the honest denominator for "how far from HBM"
+    design_frame = {("k_prep", 0): 6 * N, ("k_morph_march", 0): 2 * N + N // 8, ("k_morph_march", 1): 2 * N + N // 8,
+                    ("k_nms_march", 0): N + N // 4, ("k_nms_march", 1): N + N // 4}
     # measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per 64-frame step) of the newest committed ncu list
     import glob
     measured = {}
@@ -646,17 +650,19 @@ def run_ours(args):
         except Exception:
             pass
     ktable = [{"kernel": "k_prep", "pass": "both", "ms_per_step": prep_ms_sum / args.steps, "launches_per_step": 1,
-               "alg_bytes_per_step": B * alg_frame[("k_prep", 0)]}]
+               "alg_bytes_per_step": B * alg_frame[("k_prep", 0)], "design_bytes_per_step": B * design_frame[("k_prep", 0)]}]
     for (name, p_), (ms, nl) in sorted(kacc.items()):
         e = {"kernel": name, "pass": ("bright", "dim")[p_], "ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps}
         if (name, p_) in alg_frame:
             e["alg_bytes_per_step"] = B * alg_frame[(name, p_)]
+            e["design_bytes_per_step"] = B * design_frame[(name, p_)]
         ktable.append(e)
     for e in ktable:
         e["avg_launch_ms"] = e["ms_per_step"] / max(e["launches_per_step"], 1)
         if "alg_bytes_per_step" in e and e["ms_per_step"] > 0:
             e["gbs"] = e["alg_bytes_per_step"] / (e["ms_per_step"] * 1e6)
             e["frac_of_hbm_peak"] = e["gbs"] / peak
+            e["frac_of_hbm_peak_design_bytes"] = e["design_bytes_per_step"] / (e["ms_per_step"] * 1e6) / peak
         base = e["kernel"].split("(")[0]
         if base in measured:
             e["dram_bytes_per_step_measured_both_passes"] = measured[base]
@@ -669,6 +675,7 @@ def run_ours(args):
     dom = max((k for k in tot_by_kernel if k in hbm_kernels), key=lambda k: tot_by_kernel[k])
     dom_rows = [e for e in ktable if e["kernel"] == dom]
     dom_bytes = sum(e["alg_bytes_per_step"] for e in dom_rows)
+    dom_design_bytes = sum(e["design_bytes_per_step"] for e in dom_rows)
     dom_ms = sum(e["ms_per_step"] for e in dom_rows)
     dom_launches = sum(e["launches_per_step"] for e in dom_rows)
     # the same kernel with nothing else on the GPU: its stage brackets of the serialised steps (one launch per pass over the
@@ -679,16 +686,22 @@ def run_ours(args):
         ms_alone = sum(ms for n_, ms in stage_ms if n_.split(":")[-1].startswith(stage_of[dom]))
         if ms_alone > 0:
             alone = {"ms_per_step": ms_alone, "gbs": dom_bytes / (ms_alone * 1e6), "frac": dom_bytes / (ms_alone * 1e6) / peak,
+                     "frac_design_bytes": dom_design_bytes / (ms_alone * 1e6) / peak,
                      "how": "CUDA-event stage brackets of the %d steps run with LFD_SERIAL_PASSES (one stream, one launch per pass)" % n_serial}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e6), "peak": peak, "unit": "GB/s",
                 "frac": dom_bytes / (dom_ms * 1e6) / peak,
+                "frac_design_bytes": dom_design_bytes / (dom_ms * 1e6) / peak,
+                "design_bytes_per_launch": dom_design_bytes / dom_launches,
                 "traffic": (measured[dom] / dom_launches) if dom in measured else None,
                 "traffic_source": measured_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes / dom_launches, "avg_launch_ms": dom_ms / dom_launches,
                 "launches_per_step": dom_launches, "ms_per_step": dom_ms, "bracketed_ms_per_step": bracketed_ms_per_step,
                 "alone": alone,
                 "all_kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(tot_by_kernel.items(), key=lambda kv: -kv[1])},
-                "note": "time-dominant HBM-stage kernel (both passes, all batch parts). Durations are CUDA events recorded on the "
+                "note": "time-dominant HBM-stage kernel (both passes, all batch parts). `frac` uses SURVEY.md 8(d)'s algorithmic bytes "
+                        "(every stage charged one read of its input and one write of its output: LUT apply, erode and dilate are "
+                        "three stages there and one pass over the plane here), `frac_design_bytes` the bytes this design has to move. "
+                        "Durations are CUDA events recorded on the "
                         "launching stream around every launch inside the captured graph, over a second run of the same K steps "
                         "(bracketed_ms_per_step; the event nodes cost a few % so the headline region runs without them), with the "
                         "other three streams running - a launch timed alone is shorter (profiles/*ktiming*). The kernel is "

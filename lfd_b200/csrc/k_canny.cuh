@@ -139,6 +139,7 @@ __device__ __forceinline__ u32 vneg2(u32 a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ u32 vsub2(u32 a, u32 b) { return __vadd2(a, vneg2(b)); }
 __device__ __forceinline__ u32 vabs2s(u32 a) { return __vmaxs2(a, vneg2(a)); }
 
+// cand / strong must be zero on entry (the caller memsets them): only non-zero mask words are stored.
 template <bool TAP>
 __global__ void __launch_bounds__(NMS_WPC * 32)
 k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restrict__ cand, u32* __restrict__ strong,
@@ -180,12 +181,12 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
             for (int i = lane; i < tot; i += 32) any |= nzf[(ra + i / nw) * d.WW + i % nw];
         }
         if (!__any_sync(FULLMASK, any != 0)) {
-            for (int y = y0; y < y1; y++) {
-                if (lane < nwords) { candf[(size_t)y * d.WW + mw0 + lane] = 0u; strongf[(size_t)y * d.WW + mw0 + lane] = 0u; }
-                if (TAP)
+            // nothing to do: the candidate / strong masks are zeroed by the caller (cudaMemsetAsync) before the launch,
+            // this kernel only ever stores non-zero mask words (zero rows were 20 % of its executed instructions)
+            if (TAP)
+                for (int y = y0; y < y1; y++)
                     for (int x = lane; x < 32 * nwords; x += 32)
                         if (32 * mw0 + x < d.W) nms_tap[(size_t)f * d.N + (size_t)y * d.W + 32 * mw0 + x] = 0;
-            }
             return;
         }
     }
@@ -244,7 +245,6 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                 __syncwarp();
                 if (yn >= y0 && yn < y1) {
                     if (!nzf_any[sa]) {
-                        if (lane < nwords) { const int o = yn * d.WW + mw0 + lane; candf[o] = 0u; strongf[o] = 0u; }
                         if (TAP)
                             for (int x = lane; x < 32 * nwords; x += 32)
                                 if (32 * mw0 + x < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + 32 * mw0 + x] = 0;
@@ -327,7 +327,7 @@ k_nms_march(const u8* __restrict__ img, const u32* __restrict__ nz, u32* __restr
                         if (gi < nwords && xg < d.W) nms_tap[(size_t)f * d.N + (size_t)yn * d.W + xg] = (u8)cls;
                     }
                 }
-                if (lane < nwords) { const int o = yn * d.WW + mw0 + lane; candf[o] = myc; strongf[o] = mys; }
+                if (lane < nwords && myc) { const int o = yn * d.WW + mw0 + lane; candf[o] = myc; if (mys) strongf[o] = mys; }
             }
             __syncwarp();
         }

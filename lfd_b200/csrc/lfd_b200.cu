@@ -821,6 +821,10 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     }
     // Sobel + NMS (done by the fused kernel when that is selected)
     if (!fused) {
+    if ((d.W % 8) == 0) {        // k_nms_march stores only non-zero mask words
+        CK(cudaMemsetAsync(v_cand, 0, (size_t)n * d.NW * sizeof(u32), s));
+        CK(cudaMemsetAsync(v_strong, 0, (size_t)n * d.NW * sizeof(u32), s));
+    }
     KB_MARK(KB_NMS, 0);
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
@@ -1360,6 +1364,8 @@ extern "C" int lfd_canny(lfd_handle* h, const uint8_t* img, int low, int high, u
     if ((d.W % 8) == 0) {
         const int nstrips = ((d.W >> 2) + MARCH_UW - 1) / MARCH_UW, nchunks = (d.H + NMS_R - 1) / NMS_R;
         const int nunits = nstrips * nchunks;
+        CK(cudaMemsetAsync(h->cand[pass], 0, (size_t)d.NW * sizeof(u32), s));
+        CK(cudaMemsetAsync(h->strong[pass], 0, (size_t)d.NW * sizeof(u32), s));
         k_nms_march<false><<<dim3((nunits + NMS_WPC - 1) / NMS_WPC, n), NMS_WPC * 32, 0, s>>>(h->morph[pass], h->nz[pass], h->cand[pass], h->strong[pass], nullptr, C, pass, d,
                                                                   nstrips, nunits, low, high);
     } else {
