@@ -106,9 +106,11 @@ k_ccl_rowcount(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const Fr
             const u32 starts = cur[r] & ~((cur[r] << 1) | (prev >> 31));
             const int c = __popc(starts);
             int inc = c;
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(FULLMASK, inc, o);
-                if (lane >= o) inc += v;
+            if (__any_sync(FULLMASK, c != 0)) {              // (no run starts in these 32 words: the prefix stays at base)
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(FULLMASK, inc, o);
+                    if (lane >= o) inc += v;
+                }
             }
             if (w < d.WW && y0 + r < d.H) b.wpre[(size_t)(y0 + r) * d.WW + w] = (u16)(base[r] + inc - c);
             base[r] += __shfl_sync(FULLMASK, inc, 31);
@@ -305,6 +307,7 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     // fill: one warp per row, rows strided over the 8 warps
     for (int y = y0 + (threadIdx.x >> 5); y < y1; y += 8) {
         int rb = srb[y - y0];
+        if (srb[y - y0 + 1] == rb) continue;                      // no run in this row (most rows of a sparse edge map)
         const u32* row = sw + (y - y0) * WW;
         // words that are not all-ones, one ballot per 32-word chunk (W <= 4096 -> at most 4 chunks): a run
         // that leaves its word ends in the next such word, found with a bit scan instead of a serial walk
