@@ -328,7 +328,7 @@ def dropin_leg(device, ndistinct=32, nfields=1024, batch=32, verify=True, rank=0
     fdir = os.path.join(photoobj, "frames", "301", "2888", "1")
     odir = os.path.join(photoobj, "301", "2888", "1")
     # every rank keeps a share of the host cores for its loader threads
-    os.environ["LFD_LOADER_THREADS"] = str(max(2, min(12, (os.cpu_count() or 2) // world)))
+    os.environ["LFD_LOADER_THREADS"] = os.environ.get("LFD_BENCH_LOADERS") or str(max(2, min(12, (os.cpu_count() or 2) // world)))
     try:
         tree = None
         if rank == 0:

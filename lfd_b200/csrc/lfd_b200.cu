@@ -533,7 +533,15 @@ static int create_impl(lfd_handle* h, int device, int max_batch, int H, int W, c
         CK(cudaMemcpy(h->rbuf_d[p], h->rbuf_h[p].data(), B * sizeof(RectBuf), cudaMemcpyHostToDevice));
     }
 #undef DA
-    CK(cudaMallocHost((void**)&h->frames_h, (size_t)B * N * sizeof(float)));
+    // Pinned staging of the frames.  LFD_STAGING=wc asks for write-combined pages: the loaders' stores then bypass the
+    // caches (no read-for-ownership of lines that are only ever written by the CPU and read by the DMA engine); CPU READS of
+    // such memory are very slow, so it is only for drivers that never read the staging back (profiles/lab/h2d_lab: the
+    // copy itself runs at the same 55.5 GB/s from either kind).
+    {
+        const char* sk = getenv("LFD_STAGING");
+        if (sk && sk[0] == 'w') CK(cudaHostAlloc((void**)&h->frames_h, (size_t)B * N * sizeof(float), cudaHostAllocWriteCombined));
+        else CK(cudaMallocHost((void**)&h->frames_h, (size_t)B * N * sizeof(float)));
+    }
     CK(cudaMallocHost((void**)&h->res_h, (size_t)B * sizeof(lfd_result)));
     CK(cudaMallocHost((void**)&h->rects_h, (size_t)B * h->cfg.max_star_rects * sizeof(int4)));
     CK(cudaMallocHost((void**)&h->rect_off_h, ((size_t)B + 1) * sizeof(int)));
