@@ -460,40 +460,48 @@ def run_ours(args):
     res = hA.upload(B, rects)                          # H2D once (+ one untimed run)
     n_detect = sum(r.detected for r in res)
     pipelined = not args.serial_steps
+    depth = max(2, args.inflight) if pipelined else 1
+    hs2 = [hA, hB] + [_lib.Handle(H, W, max_batch=B, device=local) for _ in range(depth - 2)]
     if pipelined:
-        hB.upload(B, rects)                            # the second handle holds the same resident batch
-    hs2 = (hA, hB)
+        for h in hs2[1:]:
+            if h is not hB:
+                h.set_params(pb, pd)
+                for i, f in enumerate(frames):
+                    h.host_frames[i] = f
+            h.upload(B, rects)                         # every handle of the pipeline holds the same resident batch
 
     def resident_loop(steps):
-        """K steps back to back.  Pipelined (default): two handles alternate with two steps in flight, so the memory-bound
-        head of step k+1 (setup + k_prep) overlaps the latency-bound tail of step k, exactly as consecutive batches do in the
-        e2e leg and in the drop-in driver.  --serial-steps: one handle, every step collected before the next is launched."""
-        last = [None, None]
+        """K steps back to back.  Pipelined (default): `depth` handles take turns with `depth` steps in flight, so the
+        memory-bound head of step k+1 (setup + k_prep) overlaps the latency-bound tail of step k, exactly as consecutive
+        batches do in the e2e leg and in the drop-in driver.  --serial-steps: one handle, every step collected before the
+        next is launched.  Returns (results of the last step, summed k_prep ms, handle of the last step)."""
         prep = 0.0
+        res_last = None
         if not pipelined:
             for _ in range(steps):
-                hA.run_resident(B); last[0] = hA.wait()
+                hA.run_resident(B); res_last = hA.wait()
                 prep += hA.timings()[1][1]
-            return last, prep, hA
-        hs2[0].run_resident(B)
-        for k in range(1, steps):
-            hs2[k & 1].run_resident(B)
-            last[(k - 1) & 1] = hs2[(k - 1) & 1].wait()
-            prep += hs2[(k - 1) & 1].timings()[1][1]
-        last[(steps - 1) & 1] = hs2[(steps - 1) & 1].wait()
-        prep += hs2[(steps - 1) & 1].timings()[1][1]
-        return last, prep, hs2[(steps - 1) & 1]
+            return res_last, prep, hA
+        for k in range(steps):
+            if k >= depth:                             # the handle is still busy with step k - depth: collect it first
+                hs2[k % depth].wait()
+                prep += hs2[k % depth].timings()[1][1]
+            hs2[k % depth].run_resident(B)
+        for k in range(max(steps - depth, 0), steps):  # drain, oldest first
+            res_last = hs2[k % depth].wait()
+            prep += hs2[k % depth].timings()[1][1]
+        return res_last, prep, hs2[(steps - 1) % depth]
 
     resident_loop(max(args.warmup, 3))
     sampler = ClockSampler(local)
     stage_ms = None
     barrier()
     sampler.start()
-    l0 = hA.kernel_launches() + hB.kernel_launches()
+    l0 = sum(h.kernel_launches() for h in hs2)
     t0 = time.perf_counter()
     hA.timer_mark(0)
     last_res, prep_ms_sum, h_last = resident_loop(args.steps)   # k_prep runs before the passes fork: its bracket is clean
-    res_resident = [bytes(r) for r in (last_res[(args.steps - 1) & 1] if pipelined else last_res[0])]
+    res_resident = [bytes(r) for r in last_res]
     h_last.timer_mark(1)
     dev_ms = hA.timer_elapsed_ms(0, h_last, 1)        # CUDA events on the library's streams, first launch -> last result
     torch.cuda.synchronize()
@@ -501,7 +509,9 @@ def run_ours(args):
         dist.barrier()
     wall_s = time.perf_counter() - t0
     sampler.pause()
-    launches = hA.kernel_launches() + hB.kernel_launches() - l0
+    launches = sum(h.kernel_launches() for h in hs2) - l0
+    for h in hs2[2:]:
+        h.close()
     elapsed = reduce_max(dev_ms) / 1e3
     wall_s = reduce_max(wall_s)
     counters = hA.counters()
@@ -755,7 +765,7 @@ def run_ours(args):
                    "(sparse/dense/trail/satellite mix, seeded), inputs %.0f MB per step > L2 (126 MB), no L2 flush" % (B * N * 4 / 1e6),
                    "kinds": {k: kinds.count(k) for k in sorted(set(kinds))}, "detections_per_batch": int(n_detect),
                    "parallelism": "frame-sharded x%d, no collective" % world, "host_cpus_bound_per_rank": numa},
-        "timing": ("resident leg: K steps issued back to back on two handles holding the same resident batch, two steps in flight "
+        "timing": ("resident leg: K steps issued back to back on %d handles holding the same resident batch, %d steps in flight " % (depth, depth) +
                    "(the head of step k+1 overlaps the tail of step k; --serial-steps measures one step at a time); " if pipelined else
                    "resident leg: one handle, every step collected before the next is launched; ") +
                   "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside: "
@@ -976,6 +986,7 @@ def main():
                          "(15x15 dilation, fine rho), 5 = Hough/Canny microbench on 4096x4096")
     ap.add_argument("--hough-method", type=float, default=1.0, help="config4: params_dim['houghMethod'] (rho resolution, px)")
     ap.add_argument("--quick", action="store_true", help="config5: first four cases only")
+    ap.add_argument("--inflight", type=int, default=2, help="resident leg: steps (= handles) in flight (default 2)")
     ap.add_argument("--serial-steps", action="store_true",
                     help="resident leg: collect every step before launching the next (default: two handles, two steps in flight)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (target command for ncu)")
