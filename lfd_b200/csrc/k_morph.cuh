@@ -251,8 +251,11 @@ __device__ __forceinline__ u32 nzbits4(u32 w)
     return ((m >> 7) * 0x10204080u) >> 28;
 }
 
+#ifndef MARCH_MINB
+#define MARCH_MINB 1          // __launch_bounds__ min CTAs per SM (register cap) of the marching morphology kernel
+#endif
 template <int EH, int EW, int DH, int DW>
-__global__ void __launch_bounds__(MARCH_WPC * 32)
+__global__ void __launch_bounds__(MARCH_WPC * 32, MARCH_MINB)
 k_morph_march(const u8* __restrict__ gray, const u8* __restrict__ lut, u8* __restrict__ morph, u32* __restrict__ nz,
               u8* __restrict__ eroded_tap, const FrameCtl* __restrict__ ctl, int pass, Dims d, int nstrips, int nunits)
 {
