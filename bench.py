@@ -282,7 +282,9 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "frame": [H, W], "frames_per_step": per_step, "cv2": cv2.__version__, "numpy": np.__version__},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frames/step x %d steps of the %s pool, oracle/ref_pipeline.py (reference call sequence on cv2 %s), "
-                                   "multiprocessing.Pool(%d), cv2.setNumThreads(1)" % (per_step, args.steps, WORKLOAD, cv2.__version__, cores)},
+                                   "multiprocessing.Pool(%d), cv2.setNumThreads(1); the workers inherit the decoded frames by fork, a job "
+                                   "is an index (round 1 pickled 12 MB per job inside the timed region, which halved this figure)"
+                                   % (per_step, args.steps, WORKLOAD, cv2.__version__, cores)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
