@@ -144,6 +144,7 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
         u32 m = sgv.y;
         const float yf = MAGIC ? __fsub_rn(__int_as_float(0x4B000000 + y), 8388608.0f) : (float)y;
         float ys = __fmul_rn(yf, s);
+        const float x0f = MAGIC ? __fsub_rn(__int_as_float(0x4B000000 + x0), 8388608.0f) : (float)x0;
         int fb = __ffs(m) - 1, lb = 31 - __clz(m);
         int r1 = HOUGH_R(x0 + fb);
         int r2 = HOUGH_R(x0 + lb);
@@ -157,7 +158,9 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
             // two float roundings matter - is finished by bisection on the exact expression.
             const float half = (r2 > r1) ? 0.5f : -0.5f;
             auto last_with = [&](int lo, int hi, int rr) -> int {       // R(lo) == rr, R(hi) != rr  ->  largest x with R(x) == rr
-                const float xg = __fmul_rn(__fsub_rn(__fadd_rn((float)rr, half), ys), inv_c) - (float)x0;
+                // (prediction only: the conversions may be the magic ones, exact for |rr| < 2^22 and 0 <= x0 < 2^23)
+                const float rrf = MAGIC ? __fsub_rn(__int_as_float(0x4B400000 + rr), 12582912.0f) : (float)rr;
+                const float xg = __fmul_rn(__fsub_rn(__fadd_rn(rrf, half), ys), inv_c) - x0f;
                 // (a prediction only - any integer works, it is verified below - so the conversion may be the magic one too)
                 int g = MAGIC ? (__float_as_int(__fadd_rn(xg, 12582912.0f)) - 0x4B400000) : __float2int_rd(xg);
                 g = min(max(g, lo), hi - 1);
