@@ -419,8 +419,12 @@ def run_ours(args):
     if args.workload == "config5":
         return run_ours_config5(args)
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     distributed = world > 1
+    # one rank per GPU; with more GPUs visible than ranks the ranks are spread over the device indices, because GPUs with
+    # neighbouring indices share a host bridge and host->device PCIe is the pipeline's scarce link (lfd_b200/sharding.py)
+    from lfd_b200.sharding import spread_device
+    local = spread_device(local_rank, world, torch.cuda.device_count())
     torch.cuda.set_device(local)
     orig_affinity = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local)        # before any pinned allocation (first-touch places the staging pages)
@@ -766,7 +770,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "frame": [H, W], "frames_per_step_per_gpu": B, "pool": "B distinct frames per rank "
                    "(sparse/dense/trail/satellite mix, seeded), inputs %.0f MB per step > L2 (126 MB), no L2 flush" % (B * N * 4 / 1e6),
                    "kinds": {k: kinds.count(k) for k in sorted(set(kinds))}, "detections_per_batch": int(n_detect),
-                   "parallelism": "frame-sharded x%d, no collective" % world, "host_cpus_bound_per_rank": numa},
+                   "parallelism": "frame-sharded x%d, no collective" % world, "host_cpus_bound_per_rank": numa,
+                   "cuda_device_of_rank0": local, "device_map": os.environ.get("LFD_DEVICE_MAP", "spread")},
         "timing": ("resident leg: K steps issued back to back on %d handles holding the same resident batch, %d steps in flight " % (depth, depth) +
                    "(the head of step k+1 overlaps the tail of step k; --serial-steps measures one step at a time); " if pipelined else
                    "resident leg: one handle, every step collected before the next is launched; ") +

@@ -546,7 +546,11 @@ class DetectTrails:
         self.kwargs = kwargs
         self.params_bright, self.params_dim, self.params_removestars = default_params()
         self.batch = int(kwargs.get("batch", 16))
-        self.device = int(kwargs.get("device", os.environ.get("LOCAL_RANK", 0)))
+        if "device" in kwargs:
+            self.device = int(kwargs["device"])
+        else:                                          # under torchrun: LOCAL_RANK, spread over the node's GPUs (sharding.py)
+            from .sharding import spread_device
+            self.device = spread_device(os.environ.get("LOCAL_RANK", 0)) if "LOCAL_RANK" in os.environ else 0
         resume = kwargs.get("resume", None)
         self.progress = (os.path.join(savepth, "progress.txt") if resume is True else resume) or None
 

@@ -26,6 +26,30 @@ def world_size():
     return dist.get_world_size() if is_distributed() else 1
 
 
+def spread_device(local_rank, local_world=None, ngpu=None):
+    """CUDA device for a local rank when the node has more GPUs than ranks: ranks are spread evenly over the device
+    indices (rank r of N on G GPUs -> device r * (G // N)) instead of packed on devices 0..N-1.  The pipeline's scarce
+    link is host->device PCIe, and GPUs with neighbouring indices share a host bridge on the 8 x B200 boxes this was
+    measured on (profiles/h2d_lab_*.txt: devices 0-3 share ~120 GB/s, 0-7 ~235 GB/s, any two ~55 GB/s each), so four
+    ranks on devices 0, 2, 4, 6 get twice the copy bandwidth of four ranks on 0-3.  With as many ranks as GPUs (or when
+    the counts do not divide) this is the identity.  LFD_DEVICE_MAP=packed keeps device = local rank."""
+    import os
+    local_rank = int(local_rank)
+    if os.environ.get("LFD_DEVICE_MAP", "spread") == "packed":
+        return local_rank
+    try:
+        if local_world is None:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", 1)))
+        if ngpu is None:
+            import torch
+            ngpu = torch.cuda.device_count()
+    except Exception:   # noqa: BLE001
+        return local_rank
+    if local_world < 1 or ngpu <= local_world or ngpu % local_world != 0:
+        return local_rank
+    return local_rank * (ngpu // local_world)
+
+
 def shard_indices(n, rank, world, block):
     """Indices of the frames rank `rank` processes: blocks of `block` consecutive frames, round-robin over ranks
     (full GPU batches, and neighbouring fields - which share catalog/FITS directories - stay together)."""

@@ -110,3 +110,17 @@ def test_resume_skips_finished_frames(tmp_path):
     seen = [f for c in calls for f in c]
     assert sorted(seen) == sorted(frames) and len(seen) == len(set(seen))      # every frame computed exactly once
     assert len(read_progress(prog)) == len(frames)
+
+
+def test_spread_device_placement(monkeypatch):
+    """More GPUs than ranks: ranks are spread over the device indices (host->device PCIe is the scarce link and
+    neighbouring GPUs share a host bridge); as many ranks as GPUs, or counts that do not divide: identity."""
+    from lfd_b200.sharding import spread_device
+    monkeypatch.delenv("LFD_DEVICE_MAP", raising=False)
+    assert [spread_device(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]
+    assert [spread_device(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [spread_device(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [spread_device(r, 3, 8) for r in range(3)] == [0, 1, 2]
+    assert spread_device(0, 1, 8) == 0 and spread_device(0, 1, 1) == 0
+    monkeypatch.setenv("LFD_DEVICE_MAP", "packed")
+    assert [spread_device(r, 4, 8) for r in range(4)] == [0, 1, 2, 3]
