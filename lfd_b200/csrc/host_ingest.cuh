@@ -340,19 +340,25 @@ extern "C" int lfd_ingest_batch(void* staging, int height, int width, int n, con
         for (;;) {
             const int t = next.fetch_add(1, std::memory_order_relaxed);
             if (t >= 2 * n) return;
+            // nothing may propagate out of a worker thread (std::terminate): an item that throws (out of memory while
+            // reading a table) is reported like any other item the caller has to read itself
             if (t < n) {
                 const int i = t;
-                status_frame[i] = frame_paths[i] ? lfd_fits_load_frame(frame_paths[i], (char*)staging + (size_t)i * slot_bytes, height, width,
-                                                                         keys, nkeys, values + (size_t)i * nkeys * 72)
-                                                 : LFD_E_ARG;
+                try {
+                    status_frame[i] = frame_paths[i] ? lfd_fits_load_frame(frame_paths[i], (char*)staging + (size_t)i * slot_bytes, height,
+                                                                             width, keys, nkeys, values + (size_t)i * nkeys * 72)
+                                                     : LFD_E_ARG;
+                } catch (...) { status_frame[i] = LFD_E_ARG; }
             } else {
                 const int i = t - n;
                 n_rects[i] = 0;
                 const int b = bands[i];
-                status_cat[i] = (cat_paths[i] && b >= 0 && b <= 4)
-                                    ? lfd_catalog_rects(cat_paths[i], b, height, width, filter_caps[b], maxmagdiff, magcount, pixscale,
-                                                        defaultxy, maxxy, rects + (size_t)i * max_rects * 4, max_rects, &n_rects[i])
-                                    : LFD_E_ARG;
+                try {
+                    status_cat[i] = (cat_paths[i] && b >= 0 && b <= 4)
+                                        ? lfd_catalog_rects(cat_paths[i], b, height, width, filter_caps[b], maxmagdiff, magcount, pixscale,
+                                                            defaultxy, maxxy, rects + (size_t)i * max_rects * 4, max_rects, &n_rects[i])
+                                        : LFD_E_ARG;
+                } catch (...) { status_cat[i] = LFD_E_ARG; n_rects[i] = 0; }
             }
         }
     };
@@ -361,8 +367,12 @@ extern "C" int lfd_ingest_batch(void* staging, int height, int width, int n, con
     if (nt > 2 * n) nt = 2 * n;
     if (nt > 64) nt = 64;
     std::vector<std::thread> pool;
-    pool.reserve(nt - 1);
-    for (int k = 1; k < nt; k++) pool.emplace_back(work);
+    try {
+        pool.reserve(nt - 1);
+        for (int k = 1; k < nt; k++) pool.emplace_back(work);
+    } catch (...) {
+        // could not start (all of) the helpers: the calling thread and whoever did start finish the items
+    }
     work();
     for (auto& th : pool) th.join();
     return LFD_OK;

@@ -382,43 +382,59 @@ def compute_fields_iter(frames, params_bright, params_dim, params_removestars, b
                     oc.update(finish(e))
                 yield cj * batch, records_of(cj, itj, oc)
 
-        for ci, chunk in enumerate(chunks):
-            # the handle batch ci+1 loads into is the one batch ci-2 used (ring of three): collect that one, then start
-            # the next load so that it runs while batch ci is submitted and batch ci-1 computes
-            yield from drain(ci - (len(ring) - 1 if ring else 1))
-            if ci + 1 < len(chunks):
-                futs[ci + 1] = bpool.submit(load_chunk, ci + 1, fpool)
-            items = futs.pop(ci).result()
-            base = ci * batch
-            h = ring[ci % len(ring)] if ring else None
-            outcome = {}
-            entries = []
-            staged = [j for j, it in enumerate(items) if it[0] == "staged"]
-            if staged:
-                # staged frames sit in their own slots; compact them to the front (a frame that failed or took
-                # another path leaves a hole)
-                st = h.host_frames.view(_np.uint32)
-                for k, j in enumerate(staged):
-                    if k != j:
-                        st[k] = st[j]
-                entries.append(submit(h, shape0, [base + j for j in staged], [items[j][3] for j in staged], True))
-            others = {}
-            for j, it in enumerate(items):
-                if it[0] == "ok":
-                    others.setdefault((tuple(it[1].shape), bool(it[2])), []).append(j)
-            for (shape, big_endian), idxs in others.items():
-                # another frame shape (or no ring): a cached handle of that shape, run to completion right away
-                gidx = [base + j for j in idxs]
+        try:
+            for ci, chunk in enumerate(chunks):
+                # the handle batch ci+1 loads into is the one batch ci-2 used (ring of three): collect that one, then start
+                # the next load so that it runs while batch ci is submitted and batch ci-1 computes
+                yield from drain(ci - (len(ring) - 1 if ring else 1))
+                if ci + 1 < len(chunks):
+                    futs[ci + 1] = bpool.submit(load_chunk, ci + 1, fpool)
+                items = futs.pop(ci).result()
+                base = ci * batch
+                h = ring[ci % len(ring)] if ring else None
+                outcome = {}
+                entries = []
+                staged = [j for j, it in enumerate(items) if it[0] == "staged"]
+                if staged:
+                    # staged frames sit in their own slots; compact them to the front (a frame that failed or took
+                    # another path leaves a hole)
+                    st = h.host_frames.view(_np.uint32)
+                    for k, j in enumerate(staged):
+                        if k != j:
+                            st[k] = st[j]
+                    entries.append(submit(h, shape0, [base + j for j in staged], [items[j][3] for j in staged], True))
+                others = {}
+                for j, it in enumerate(items):
+                    if it[0] == "ok":
+                        others.setdefault((tuple(it[1].shape), bool(it[2])), []).append(j)
+                for (shape, big_endian), idxs in others.items():
+                    # another frame shape (or no ring): a cached handle of that shape, run to completion right away
+                    gidx = [base + j for j in idxs]
+                    try:
+                        hh = _batch_handles(shape, batch, device, count=1)[0]
+                        stg = hh.host_frames.view(_np.uint32) if big_endian else hh.host_frames
+                        for slot, j in enumerate(idxs):
+                            stg[slot] = items[j][1]
+                        outcome.update(finish(submit(hh, shape, gidx, [items[j][3] for j in idxs], big_endian)))
+                    except Exception as e:   # noqa: BLE001
+                        outcome.update({g: ("err", e) for g in gidx})
+                inflight.append((ci, items, entries, outcome))
+            yield from drain(len(chunks))
+        finally:
+            # the consumer stopped early (or something raised): collect what is still on the GPU, so that the cached
+            # handles are not left with a pending batch ("previous batch not collected" on their next use)
+            for _cj, _itj, ents, _oc in inflight:
+                for e in ents:
+                    if e[0] == "entry":
+                        try:
+                            e[1].wait()
+                        except Exception:   # noqa: BLE001
+                            pass
+            for fu in futs.values():
                 try:
-                    hh = _batch_handles(shape, batch, device, count=1)[0]
-                    stg = hh.host_frames.view(_np.uint32) if big_endian else hh.host_frames
-                    for slot, j in enumerate(idxs):
-                        stg[slot] = items[j][1]
-                    outcome.update(finish(submit(hh, shape, gidx, [items[j][3] for j in idxs], big_endian)))
-                except Exception as e:   # noqa: BLE001
-                    outcome.update({g: ("err", e) for g in gidx})
-            inflight.append((ci, items, entries, outcome))
-        yield from drain(len(chunks))
+                    fu.result()                       # a loader still writing into a handle's staging
+                except Exception:   # noqa: BLE001
+                    pass
 
 
 def compute_fields(frames, params_bright, params_dim, params_removestars, batch=16, device=0, loaders=None):
