@@ -178,3 +178,31 @@ def test_dropin_bz2_frames_and_overflow_retry(tmp_path, cv2mod, monkeypatch):
     monkeypatch.setattr(dtm, "_big_handle", lambda shape, device: (calls.append(shape), real(shape, device))[1])
     assert run("tiny") == (exp, "")
     assert len(calls) >= 2, "no frame overflowed: the retry path was not exercised"
+
+
+def test_production_batch_config4_matches_oracle(cv2mod):
+    """BASELINE.json config 4 through the production path (B = 64, no tap flags): high-sensitivity dim pass with a 15x15
+    dilation kernel and rho = 1 px (numrho = 7075: two angles per vote CTA, per-pixel voting, single privatised copy);
+    every verdict equals the oracle's with the same parameters."""
+    from lfd_b200 import _lib
+    from lfd_b200.removestars import star_rects
+    B = 64
+    frames, cats, filters, kinds = _pool(40, 24)
+    pb = dict(rp.DEFAULT_BRIGHT)
+    pd = dict(rp.DEFAULT_DIM, dilateKernel=np.ones((15, 15), np.uint8), houghMethod=1)
+    pr = dict(rp.DEFAULT_REMOVESTARS)
+    ref = verdicts(frames, cats, filters, pb, pd, pr)
+    rects = [star_rects(c, flt, f.shape, **pr) for f, c, flt in zip(frames, cats, filters)]
+    h = _lib.Handle(synth.FRAME_H, synth.FRAME_W, max_batch=B)
+    try:
+        h.set_params(pb, pd)
+        for j in range(B):
+            h.host_frames[j] = frames[j]
+        h.submit(B, rects)
+        res = h.wait()
+        bad = ["frame %d (%s): got %s, oracle %s" % (i, kinds[i], device_verdict(res[i], frames[0].shape), ref[i])
+               for i in range(B) if device_verdict(res[i], frames[0].shape) != tuple(ref[i])]
+        assert not bad, "\n".join(bad[:10])
+        assert sum(1 for r in ref if r[0] is True and r[1] == 1) >= 2, "no dim-pass detection in the pool"
+    finally:
+        h.close()
