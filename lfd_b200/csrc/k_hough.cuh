@@ -130,10 +130,9 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
     // a blob vote for the same bins at the same moment, and same-address shared-memory atomics serialise.
     const int S = (nseg + per - 1) / per;              // words per slice
     const int step = nwarps;
-    auto fetch = [&](int si) -> uint2 {
-        const int idx = si + sub * S;
-        return (live && si < S && idx < nseg) ? __ldg(sg + idx) : make_uint2(0u, 0u);
-    };
+    const uint2* const sgp = sg + sub * S;             // this lane's slice ...
+    const int lim = live ? min(S, nseg - sub * S) : 0; // ... and how many words of it exist
+    auto fetch = [&](int si) -> uint2 { return si < lim ? __ldg(sgp + si) : make_uint2(0u, 0u); };
     uint2 q0 = fetch(warp), q1 = fetch(warp + step);
     for (int si = warp; si < S; si += step) {
         const uint2 sgv = q0;
@@ -178,7 +177,8 @@ k_hough_vote(const uint2* __restrict__ segs, int* __restrict__ accum, const floa
             const int lo = last_with(fb, lb, r1), hi = lo + 1;
             int c1 = __popc(m & bit_range(fb, lo));
             HVOTE(r1, c1);
-            int rm = HOUGH_R(x0 + hi);
+            // two adjacent bins and a monotone r: what follows the last pixel of r1 is r2, no evaluation needed
+            int rm = (abs(r2 - r1) == 1) ? r2 : HOUGH_R(x0 + hi);
             if (rm == r2) {
                 HVOTE(r2, __popc(m & bit_range(hi, lb)));
             } else {
