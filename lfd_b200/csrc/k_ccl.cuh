@@ -267,10 +267,21 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     if (ctl[f].nruns[kind] == 0) return;
     const u32* m = mask + (size_t)f * d.NW;
     CclBuf b = bufs[f];
+    extern __shared__ u32 band_sm[];
+    // One band per CTA.  (CCL_BAND_CTAS, a lab knob: at most that many CTAs per frame, each looping over its bands - what
+    // a cluster-synchronised single CCL kernel would have to live with; measured in DESIGN.md section 7.)
+#ifdef CCL_BAND_CTAS
+    for (int band = blockIdx.x; band * CCL_BAND < d.H; band += gridDim.x) {
+    __syncthreads();
+    const int y0 = band * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
+    const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
+    if (nb == 0) continue;
+#else
+    {
     const int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
     const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
     if (nb == 0) return;
-    extern __shared__ u32 band_sm[];
+#endif
     u32* sw = band_sm;                                        // [CCL_BAND][WW]
     int* sp = (int*)(band_sm + CCL_BAND * d.WW);              // [CCL_BAND_CAP]
     Run* srun = (Run*)(sp + CCL_BAND_CAP);                    // [CCL_BAND_CAP]
@@ -394,6 +405,7 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     } else {
         for (int i = threadIdx.x; i < nb; i += blockDim.x) b.parent[base + i] = uf_find_ro(b.parent, base + i);
     }
+    }   // band
 }
 
 // 4b. stitch the bands: rows y = k * CCL_BAND against row y-1; one warp per seam
