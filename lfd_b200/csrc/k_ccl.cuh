@@ -214,6 +214,9 @@ __device__ __forceinline__ void link_rows(const u32* __restrict__ m, const CclBu
 }
 
 #define CCL_BAND 32
+#ifndef CCL_BAND_CTAS
+#define CCL_BAND_CTAS 16          // CTAs per frame of k_ccl_band in launches of >= 16 frames
+#endif
 
 // ---- shared-memory union-find (band-local): same algorithm as uf_find / uf_union on a __shared__ array
 __device__ __forceinline__ int suf_find(volatile int* p, int i)
@@ -268,20 +271,15 @@ k_ccl_band(const u32* __restrict__ mask, CclBuf* __restrict__ bufs, const FrameC
     const u32* m = mask + (size_t)f * d.NW;
     CclBuf b = bufs[f];
     extern __shared__ u32 band_sm[];
-    // One band per CTA.  (CCL_BAND_CTAS, a lab knob: at most that many CTAs per frame, each looping over its bands - what
-    // a cluster-synchronised single CCL kernel would have to live with; measured in DESIGN.md section 7.)
-#ifdef CCL_BAND_CTAS
+    // A CTA takes the bands blockIdx.x, blockIdx.x + gridDim.x, ...: one band per CTA when a few frames are in the launch
+    // (shortest latency), CCL_BAND_CTAS bands-looping CTAs per frame in big batches, where the per-CTA prologue (11 % of the
+    // kernel's instructions with one band per CTA) is what counts: +1.4 % frames/s on the pipelined 64-frame step, while the
+    // launch alone gets 1.2-1.5x longer.
     for (int band = blockIdx.x; band * CCL_BAND < d.H; band += gridDim.x) {
     __syncthreads();
     const int y0 = band * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
     const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
     if (nb == 0) continue;
-#else
-    {
-    const int y0 = blockIdx.x * CCL_BAND, y1 = min(y0 + CCL_BAND, d.H);
-    const int base = b.rowbase[y0], nb = b.rowbase[y1] - base;
-    if (nb == 0) return;
-#endif
     u32* sw = band_sm;                                        // [CCL_BAND][WW]
     int* sp = (int*)(band_sm + CCL_BAND * d.WW);              // [CCL_BAND_CAP]
     Run* srun = (Run*)(sp + CCL_BAND_CAP);                    // [CCL_BAND_CAP]

@@ -758,11 +758,7 @@ static int run_pass_kernels(lfd_handle* h, int f0, int n, int pass, int flags, c
     HoughBufs& hb = h->hb[pass];
     dim3 rows((d.H + CCL_WARPS * CCL_RC_ROWS - 1) / (CCL_WARPS * CCL_RC_ROWS), n);
     const int nbands = (d.H + CCL_BAND - 1) / CCL_BAND;
-#ifdef CCL_BAND_CTAS
-    dim3 bands(nbands < CCL_BAND_CTAS ? nbands : CCL_BAND_CTAS, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
-#else
-    dim3 bands(nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
-#endif
+    dim3 bands((n >= 16 && nbands > CCL_BAND_CTAS) ? CCL_BAND_CTAS : nbands, n), seams((nbands + CCL_WARPS - 1) / CCL_WARPS, n);
 
     // NMS tap (class per pixel) only with LFD_KEEP_TAPS
     u8* ntap = nullptr;
