@@ -457,8 +457,14 @@ def run_ours(args):
     _CPU_PARAMS = (pb, pd)
     hA = _lib.Handle(H, W, max_batch=B, device=local)
     hB = _lib.Handle(H, W, max_batch=B, device=local)
+    # more than two ranks behind one PCIe host bridge: the ranks of a bridge slot take turns with their batch copies
+    # (lfd_b200/sharding.py::h2d_gate_path; None on one or two ranks per bridge)
+    from lfd_b200.sharding import h2d_gate_path
+    gate = h2d_gate_path(local, world, torch.cuda.device_count()) if distributed else None
     for h in (hA, hB):
         h.set_params(pb, pd)
+        if gate:
+            h.set_h2d_gate(gate)
         for i, f in enumerate(frames):
             h.host_frames[i] = f                       # pinned host staging, filled once
 
@@ -771,7 +777,8 @@ def run_ours(args):
                    "(sparse/dense/trail/satellite mix, seeded), inputs %.0f MB per step > L2 (126 MB), no L2 flush" % (B * N * 4 / 1e6),
                    "kinds": {k: kinds.count(k) for k in sorted(set(kinds))}, "detections_per_batch": int(n_detect),
                    "parallelism": "frame-sharded x%d, no collective" % world, "host_cpus_bound_per_rank": numa,
-                   "cuda_device_of_rank0": local, "device_map": os.environ.get("LFD_DEVICE_MAP", "spread")},
+                   "cuda_device_of_rank0": local, "device_map": os.environ.get("LFD_DEVICE_MAP", "spread"),
+                   "h2d_gate_of_rank0": gate},
         "timing": ("resident leg: K steps issued back to back on %d handles holding the same resident batch, %d steps in flight " % (depth, depth) +
                    "(the head of step k+1 overlaps the tail of step k; --serial-steps measures one step at a time); " if pipelined else
                    "resident leg: one handle, every step collected before the next is launched; ") +

@@ -160,6 +160,15 @@ const char* lfd_last_error(const lfd_handle* h);   /* h may be NULL: error of th
 
 int lfd_set_params(lfd_handle* h, const lfd_params* p);
 
+/* Multi-GPU nodes: share a host->device copy slot with other processes.  `lock_path` names an advisory lock file; the
+ * handle takes the lock (waiting at most 250 ms) before it enqueues a batch's H2D copy in lfd_submit / lfd_upload and a
+ * stream callback releases it when the copy has completed, so at most one of the handles naming the same file copies at a
+ * time.  With several GPUs behind one PCIe host bridge this makes the bridge's bandwidth shares equal (the Python driver
+ * and bench.py name two slots per bridge when more than two ranks share one: lfd_b200/sharding.py::h2d_gate_path).
+ * NULL or "" removes the gate.  The reference has no counterpart (its scale-out is one PBS job per run,
+ * lfd/createjobs/createjobs.py:173-218). */
+int lfd_set_h2d_gate(lfd_handle* h, const char* lock_path);
+
 /* Structuring elements that are not all-ones rectangles (cv2.getStructuringElement crosses / ellipses, hand-made
  * masks), for one pass: row-major uint8 masks, non-zero = member, cv2's default anchor (kw/2, kh/2), sides 1..31.
  * Call after lfd_set_params (which resets both passes to the all-ones rectangles of lfd_pass_params).

@@ -100,6 +100,7 @@ def lib():
                                     ctypes.POINTER(ctypes.c_void_p)]
         L.lfd_destroy.argtypes = [ctypes.c_void_p]
         L.lfd_set_params.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.lfd_set_h2d_gate.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.lfd_set_kernels.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.lfd_host_frames.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
@@ -288,6 +289,11 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def set_h2d_gate(self, lock_path):
+        """Share a host->device copy slot (an advisory lock file) with the other ranks behind the same host bridge;
+        None removes the gate (include/lfd_b200.h: lfd_set_h2d_gate)."""
+        self._ck(self._L.lfd_set_h2d_gate(self.h, os.fsencode(lock_path) if lock_path else None))
 
     def set_params(self, params_bright, params_dim):
         key = repr((sorted((k, np.asarray(v).tolist()) for k, v in params_bright.items() if k != "debug"),

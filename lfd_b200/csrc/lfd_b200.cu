@@ -10,6 +10,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/file.h>
+#include <time.h>
+#include <unistd.h>
+
 #include <string>
 #include <vector>
 
@@ -75,6 +80,10 @@ struct lfd_handle {
     cudaEvent_t xjoin[LFD_MAX_SPLIT][2];
     cudaEvent_t ev_fork = nullptr;
     int nsplit_cfg = 2;                   // env LFD_NSPLIT (1..LFD_MAX_SPLIT)
+    // host->device copy gate (lfd_set_h2d_gate): an advisory file lock shared with the other ranks of the same host bridge
+    // slot, held from the moment the batch copy is enqueued until it has completed (released by a stream host callback)
+    int gate_fd = -1;
+    int64_t gate_waits = 0, gate_timeouts = 0;
     std::string err;
     int64_t launches = 0;
     int last_n = 0, last_flags = 0;
@@ -352,6 +361,7 @@ extern "C" int lfd_destroy(lfd_handle* h)
     for (int k = 0; k < LFD_MAX_SPLIT; k++)
         for (int p = 0; p < 2; p++)
             if (h->xs[k][p] && h->xs[k][p] != h->stream) cudaStreamSynchronize(h->xs[k][p]);
+    if (h->gate_fd >= 0) { flock(h->gate_fd, LOCK_UN); close(h->gate_fd); h->gate_fd = -1; }
     for (void* p : h->allocs) cudaFree(p);
     for (int p = 0; p < 2; p++) {
         if (h->hb[p].accum) cudaFree(h->hb[p].accum);
@@ -1033,6 +1043,8 @@ static int run_pipeline(lfd_handle* h, int n, int flags, int mode, bool want_cli
     return LFD_OK;
 }
 
+static void CUDART_CB gate_release_cb(void* p) { flock((int)(intptr_t)p, LOCK_UN); }
+
 static int stage_rects(lfd_handle* h, int n, const int32_t* rects, const int32_t* rect_offsets)
 {
     if (!rects || !rect_offsets) {
@@ -1059,8 +1071,42 @@ extern "C" int lfd_upload(lfd_handle* h, const float* frames, int n, const int32
     int rc = stage_rects(h, n, rects, rect_offsets);
     if (rc != LFD_OK) return rc;
     const float* src = frames ? frames : h->frames_h;
-    CK(cudaMemcpyAsync(h->in, src, (size_t)n * h->d.N * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // Copy gate: wait (bounded) for this rank's slot of its host bridge, copy, and let a host callback on the stream free
+    // the slot when the copy has completed.  With four GPUs behind one ~117 GB/s bridge the four concurrent 781 MB copies
+    // are served unfairly (21-37 GB/s per GPU, profiles/h2d_lab_g8.txt) and the slowest rank sets the pace of a job that
+    // gives every rank the same work; two copies at a time run at ~55 GB/s each and every rank gets the same share.
+    bool held = false;
+    if (h->gate_fd >= 0) {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (;;) {
+            if (flock(h->gate_fd, LOCK_EX | LOCK_NB) == 0) { held = true; break; }
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if ((t1.tv_sec - t0.tv_sec) * 1000.0 + (t1.tv_nsec - t0.tv_nsec) / 1e6 > 250.0) { h->gate_timeouts++; break; }   // never deadlock on a peer
+            usleep(40);
+        }
+        h->gate_waits++;
+    }
+    cudaError_t ce = cudaMemcpyAsync(h->in, src, (size_t)n * h->d.N * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (held) {
+        if (ce != cudaSuccess || cudaLaunchHostFunc(h->stream, gate_release_cb, (void*)(intptr_t)h->gate_fd) != cudaSuccess)
+            flock(h->gate_fd, LOCK_UN);
+    }
+    if (ce != cudaSuccess) { h->err = std::string("cudaMemcpyAsync(H2D): ") + cudaGetErrorString(ce); return LFD_E_CUDA; }
     h->last_flags = flags;
+    return LFD_OK;
+}
+
+// Share the host->device copy slot named by `lock_path` (an advisory lock file, created if missing) with the other
+// processes that name the same file; NULL or "" removes the gate.  See lfd_upload.
+extern "C" int lfd_set_h2d_gate(lfd_handle* h, const char* lock_path)
+{
+    if (!h) return LFD_E_ARG;
+    if (h->gate_fd >= 0) { flock(h->gate_fd, LOCK_UN); close(h->gate_fd); h->gate_fd = -1; }
+    if (!lock_path || !lock_path[0]) return LFD_OK;
+    int fd = open(lock_path, O_RDWR | O_CREAT | O_CLOEXEC, 0666);
+    if (fd < 0) { h->err = std::string("lfd_set_h2d_gate: cannot open ") + lock_path; return LFD_E_ARG; }
+    h->gate_fd = fd;
     return LFD_OK;
 }
 

@@ -50,6 +50,39 @@ def spread_device(local_rank, local_world=None, ngpu=None):
     return local_rank * (ngpu // local_world)
 
 
+BRIDGE_GPUS = 4      # GPUs per PCIe host bridge on the 8 x B200 boxes measured (profiles/h2d_lab_subsets.txt)
+BRIDGE_SLOTS = 2     # concurrent batch copies a bridge serves at full speed (two GPUs: 55.5 GB/s each; four: 21-37 GB/s)
+
+
+def h2d_gate_path(device, local_world=None, ngpu=None):
+    """Lock file of the host->device copy slot this rank shares with its bridge neighbours, or None when no gate is needed.
+
+    When more than BRIDGE_SLOTS ranks of this node use GPUs of one host bridge (devices 4k .. 4k+3), their concurrent
+    781 MB batch copies are served unfairly and the slowest rank sets the pace of an equal-work job; the ranks of a bridge
+    are then dealt round-robin to BRIDGE_SLOTS slots and `Handle.set_h2d_gate` makes the ranks of a slot take turns.
+    LFD_H2D_GATE=0 disables this, LFD_H2D_GATE=1 forces a gate even for one or two ranks per bridge."""
+    import os
+    import tempfile
+    mode = os.environ.get("LFD_H2D_GATE", "auto")
+    if mode == "0":
+        return None
+    try:
+        if local_world is None:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", 1)))
+        if ngpu is None:
+            import torch
+            ngpu = torch.cuda.device_count()
+    except Exception:   # noqa: BLE001
+        return None
+    devs = [spread_device(r, local_world, ngpu) for r in range(local_world)]
+    bridge = int(device) // BRIDGE_GPUS
+    on_bridge = sorted(d for d in devs if d // BRIDGE_GPUS == bridge)
+    if int(device) not in on_bridge or (len(on_bridge) <= BRIDGE_SLOTS and mode != "1"):
+        return None
+    slot = on_bridge.index(int(device)) % BRIDGE_SLOTS
+    return os.path.join(tempfile.gettempdir(), "lfd_b200_h2d_gate_%d_%d_%d" % (os.getuid(), bridge, slot))
+
+
 def shard_indices(n, rank, world, block):
     """Indices of the frames rank `rank` processes: blocks of `block` consecutive frames, round-robin over ranks
     (full GPU batches, and neighbouring fields - which share catalog/FITS directories - stay together)."""

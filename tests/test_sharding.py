@@ -124,3 +124,18 @@ def test_spread_device_placement(monkeypatch):
     assert spread_device(0, 1, 8) == 0 and spread_device(0, 1, 1) == 0
     monkeypatch.setenv("LFD_DEVICE_MAP", "packed")
     assert [spread_device(r, 4, 8) for r in range(4)] == [0, 1, 2, 3]
+
+
+def test_h2d_gate_policy(monkeypatch):
+    """Two copy slots per host bridge (devices 4k .. 4k+3) once more than two ranks share one; none otherwise."""
+    from lfd_b200.sharding import h2d_gate_path
+    monkeypatch.delenv("LFD_H2D_GATE", raising=False)
+    monkeypatch.delenv("LFD_DEVICE_MAP", raising=False)
+    paths = [h2d_gate_path(d, 8, 8) for d in range(8)]
+    assert all(paths) and paths[0] == paths[2] != paths[1] == paths[3] and paths[4] == paths[6] != paths[5] == paths[7]
+    assert len(set(paths)) == 4 and paths[0] != paths[4]
+    assert [h2d_gate_path(d, 4, 8) for d in (0, 2, 4, 6)] == [None] * 4        # spread: two ranks per bridge
+    assert h2d_gate_path(0, 1, 8) is None and h2d_gate_path(0, 2, 8) is None
+    assert all(h2d_gate_path(d, 4, 4) for d in range(4))                         # four ranks on one bridge
+    monkeypatch.setenv("LFD_H2D_GATE", "0")
+    assert h2d_gate_path(0, 8, 8) is None
