@@ -15,7 +15,9 @@ import lfd_b200
 from lfd_b200 import synth
 
 out = sys.argv[1] if len(sys.argv) > 1 else "."
-local = int(os.environ.get("LOCAL_RANK", 0))
+from lfd_b200.sharding import spread_device
+
+local = spread_device(os.environ.get("LOCAL_RANK", 0))     # the device DetectTrails picks too: ranks spread over the host bridges
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 root = os.path.join(out, "tree")
