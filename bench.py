@@ -459,12 +459,10 @@ def run_ours(args):
     hB = _lib.Handle(H, W, max_batch=B, device=local)
     # more than two ranks behind one PCIe host bridge: the ranks of a bridge slot take turns with their batch copies
     # (lfd_b200/sharding.py::h2d_gate_path; None on one or two ranks per bridge)
-    from lfd_b200.sharding import h2d_gate_path
-    gate = h2d_gate_path(local, world, torch.cuda.device_count()) if distributed else None
+    from lfd_b200.sharding import apply_h2d_gate
+    gate = apply_h2d_gate((hA, hB), local, world, torch.cuda.device_count()) if distributed else None
     for h in (hA, hB):
         h.set_params(pb, pd)
-        if gate:
-            h.set_h2d_gate(gate)
         for i, f in enumerate(frames):
             h.host_frames[i] = f                       # pinned host staging, filled once
 

@@ -202,11 +202,8 @@ def _batch_handles(shape, batch, device, count=N_RING):
         mr, mc = _handle_caps()
         hs = [_lib.Handle(shape[0], shape[1], max_batch=batch, device=device, max_runs=mr, max_components=mc) for _ in range(count)]
         if "LOCAL_RANK" in os.environ:                 # torchrun: share the bridge's copy slots with the neighbouring ranks
-            from .sharding import h2d_gate_path
-            gate = h2d_gate_path(device)
-            if gate:
-                for h in hs:
-                    h.set_h2d_gate(gate)
+            from .sharding import apply_h2d_gate
+            apply_h2d_gate(hs, device)
         _handles[key] = hs
     return hs
 

@@ -83,6 +83,27 @@ def h2d_gate_path(device, local_world=None, ngpu=None):
     return os.path.join(tempfile.gettempdir(), "lfd_b200_h2d_gate_%d_%d_%d" % (os.getuid(), bridge, slot))
 
 
+def apply_h2d_gate(handles, device, local_world=None, ngpu=None):
+    """Give `handles` the copy slot of `device` (h2d_gate_path); returns the lock path in use or None.  The gate is an
+    optimisation: a lock file that cannot be opened (read-only or foreign /tmp) leaves the handles ungated with a warning."""
+    gate = h2d_gate_path(device, local_world, ngpu)
+    if not gate:
+        return None
+    try:
+        for h in handles:
+            h.set_h2d_gate(gate)
+    except Exception as e:   # noqa: BLE001
+        import warnings
+        warnings.warn("lfd_b200: host->device copy gate disabled (%s)" % e)
+        for h in handles:
+            try:
+                h.set_h2d_gate(None)
+            except Exception:   # noqa: BLE001
+                pass
+        return None
+    return gate
+
+
 def shard_indices(n, rank, world, block):
     """Indices of the frames rank `rank` processes: blocks of `block` consecutive frames, round-robin over ranks
     (full GPU batches, and neighbouring fields - which share catalog/FITS directories - stay together)."""

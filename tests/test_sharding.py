@@ -139,3 +139,31 @@ def test_h2d_gate_policy(monkeypatch):
     assert all(h2d_gate_path(d, 4, 4) for d in range(4))                         # four ranks on one bridge
     monkeypatch.setenv("LFD_H2D_GATE", "0")
     assert h2d_gate_path(0, 8, 8) is None
+
+
+def test_apply_h2d_gate_degrades(monkeypatch):
+    """A lock file that cannot be opened leaves the handles ungated (warning), it does not abort the run."""
+    import warnings
+    from lfd_b200.sharding import apply_h2d_gate, h2d_gate_path
+    monkeypatch.delenv("LFD_H2D_GATE", raising=False)
+    monkeypatch.delenv("LFD_DEVICE_MAP", raising=False)
+
+    class Fake:
+        def __init__(self, fail):
+            self.fail, self.calls = fail, []
+
+        def set_h2d_gate(self, path):
+            self.calls.append(path)
+            if path and self.fail:
+                raise OSError("cannot open " + path)
+
+    good = [Fake(False), Fake(False)]
+    path = apply_h2d_gate(good, 1, 8, 8)
+    assert path == h2d_gate_path(1, 8, 8) and all(h.calls == [path] for h in good)
+    assert apply_h2d_gate(good, 0, 2, 8) is None and all(len(h.calls) == 1 for h in good)     # no gate needed: untouched
+    bad = [Fake(False), Fake(True)]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert apply_h2d_gate(bad, 1, 8, 8) is None
+    assert w and "gate disabled" in str(w[0].message)
+    assert bad[0].calls[-1] is None and bad[1].calls[-1] is None
