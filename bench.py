@@ -649,8 +649,8 @@ def run_ours(args):
     has_erode = pd.get("erodeKernel") is not None
     # ALGORITHMIC bytes per frame (one compulsory read of the stage input + one write of its output):
     #   S1 prep 4N read + 1N write per pass (one launch produces both passes: 4N + 2N), S2 LUT apply 2N, S3 erode 2N
-    #   (dim), S4 dilate 2N, S5 Sobel+NMS 2N.  CCL / rectangles / Hough are not HBM-bound in this design (run lists and
-    #   shared-memory accumulators): they carry measured DRAM bytes only, no roofline fraction.
+    #   (dim), S4 dilate 2N, S5 Sobel+NMS 2N, S6 labelling 9N (below).  Rectangles / Hough work on run lists and
+    #   shared-memory accumulators: they carry measured DRAM bytes only.  A pass is charged the frames it ran on.
     alg_frame = {("k_prep", 0): 6 * N, ("k_morph_march", 0): 4 * N, ("k_morph_march", 1): (6 if has_erode else 4) * N,
                  ("k_nms_march", 0): 2 * N, ("k_nms_march", 1): 2 * N}
     # what THIS design has to move per frame for the same stages (the LUT is applied inside the morphology kernel, erode and
@@ -669,64 +669,24 @@ def run_ours(args):
                 break
         except Exception:
             pass
+    runs_per_frame_pass = {"fg": counters["runs_fg"] / max(n_bright + n_dim, 1), "bg": counters["runs_bg"] / max(n_bright + n_dim, 1)}
+    for p_ in (0, 1):
+        # S6 (labelling, fg + bg): read 1N, write two int32 label planes = 9N per pass in the survey's model; this design
+        # labels RUNS: the band kernel reads the 1-bit mask (N/8) and the per-word run prefix (N/16) and writes ~12 B per run
+        alg_frame[("k_ccl_band(fg)", p_)] = 5 * N
+        alg_frame[("k_ccl_band(bg)", p_)] = 4 * N
+        for kind in ("fg", "bg"):
+            design_frame[("k_ccl_band(%s)" % kind, p_)] = N // 8 + N // 16 + int(12 * runs_per_frame_pass[kind])
+    frames_of_pass = {0: n_bright, 1: n_dim}
     ktable = [{"kernel": "k_prep", "pass": "both", "ms_per_step": prep_ms_sum / args.steps, "launches_per_step": 1,
                "alg_bytes_per_step": B * alg_frame[("k_prep", 0)], "design_bytes_per_step": B * design_frame[("k_prep", 0)]}]
     for (name, p_), (ms, nl) in sorted(kacc.items()):
         e = {"kernel": name, "pass": ("bright", "dim")[p_], "ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps}
         if (name, p_) in alg_frame:
-            e["alg_bytes_per_step"] = B * alg_frame[(name, p_)]
-            e["design_bytes_per_step"] = B * design_frame[(name, p_)]
+            e["alg_bytes_per_step"] = frames_of_pass[p_] * alg_frame[(name, p_)]
+            e["design_bytes_per_step"] = frames_of_pass[p_] * design_frame[(name, p_)]
         ktable.append(e)
-    for e in ktable:
-        e["avg_launch_ms"] = e["ms_per_step"] / max(e["launches_per_step"], 1)
-        if "alg_bytes_per_step" in e and e["ms_per_step"] > 0:
-            e["gbs"] = e["alg_bytes_per_step"] / (e["ms_per_step"] * 1e6)
-            e["frac_of_hbm_peak"] = e["gbs"] / peak
-            e["frac_of_hbm_peak_design_bytes"] = e["design_bytes_per_step"] / (e["ms_per_step"] * 1e6) / peak
-        base = e["kernel"].split("(")[0]
-        if base in measured:
-            e["dram_bytes_per_step_measured_both_passes"] = measured[base]
-    ktable.sort(key=lambda e: -e["ms_per_step"])
-    # kernels of both passes together: which kernel carries the most time
-    tot_by_kernel = {}
-    for e in ktable:
-        tot_by_kernel[e["kernel"]] = tot_by_kernel.get(e["kernel"], 0.0) + e["ms_per_step"]
-    hbm_kernels = {"k_prep", "k_morph_march", "k_nms_march"}
-    dom = max((k for k in tot_by_kernel if k in hbm_kernels), key=lambda k: tot_by_kernel[k])
-    dom_rows = [e for e in ktable if e["kernel"] == dom]
-    dom_bytes = sum(e["alg_bytes_per_step"] for e in dom_rows)
-    dom_design_bytes = sum(e["design_bytes_per_step"] for e in dom_rows)
-    dom_ms = sum(e["ms_per_step"] for e in dom_rows)
-    dom_launches = sum(e["launches_per_step"] for e in dom_rows)
-    # the same kernel with nothing else on the GPU: its stage brackets of the serialised steps (one launch per pass over the
-    # whole batch) - what the kernel itself achieves, next to what it achieves while sharing the SMs with three other streams
-    alone = None
-    stage_of = {"k_nms_march": "sobel+nms", "k_morph_march": "lut+morph"}
-    if dom in stage_of:
-        ms_alone = sum(ms for n_, ms in stage_ms if n_.split(":")[-1].startswith(stage_of[dom]))
-        if ms_alone > 0:
-            alone = {"ms_per_step": ms_alone, "gbs": dom_bytes / (ms_alone * 1e6), "frac": dom_bytes / (ms_alone * 1e6) / peak,
-                     "frac_design_bytes": dom_design_bytes / (ms_alone * 1e6) / peak,
-                     "how": "CUDA-event stage brackets of the %d steps run with LFD_SERIAL_PASSES (one stream, one launch per pass)" % n_serial}
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e6), "peak": peak, "unit": "GB/s",
-                "frac": dom_bytes / (dom_ms * 1e6) / peak,
-                "frac_design_bytes": dom_design_bytes / (dom_ms * 1e6) / peak,
-                "design_bytes_per_launch": dom_design_bytes / dom_launches,
-                "traffic": (measured[dom] / dom_launches) if dom in measured else None,
-                "traffic_source": measured_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes / dom_launches, "avg_launch_ms": dom_ms / dom_launches,
-                "launches_per_step": dom_launches, "ms_per_step": dom_ms, "bracketed_ms_per_step": bracketed_ms_per_step,
-                "alone": alone,
-                "all_kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(tot_by_kernel.items(), key=lambda kv: -kv[1])},
-                "note": "time-dominant HBM-stage kernel (both passes, all batch parts). `frac` uses SURVEY.md 8(d)'s algorithmic bytes "
-                        "(every stage charged one read of its input and one write of its output: LUT apply, erode and dilate are "
-                        "three stages there and one pass over the plane here), `frac_design_bytes` the bytes this design has to move. "
-                        "Durations are CUDA events recorded on the "
-                        "launching stream around every launch inside the captured graph, over a second run of the same K steps "
-                        "(bracketed_ms_per_step; the event nodes cost a few % so the headline region runs without them), with the "
-                        "other three streams running - a launch timed alone is shorter (profiles/*ktiming*). The kernel is "
-                        "latency / issue-bound, not HBM-bound: see profiles/ for its ncu counters. `kernels` lists every "
-                        "bracketed kernel."}
+    roofline, ktable = build_roofline(ktable, peak, peak_src, measured, measured_src, stage_ms, n_serial, bracketed_ms_per_step)
     stage_report = []
     alg_stage = {"lut+morph": 4 * N, "dim:lut+morph": (6 if has_erode else 4) * N, "sobel+nms": 2 * N}
     for name, ms in stage_ms:
@@ -808,8 +768,8 @@ def run_ours(args):
                   "rho": [float(pb["houghMethod"]), float(pd["houghMethod"])],
                   "note": "votes = non-zero pixels x 180 angles of the frames that reach HoughLines. The kernel issues one shared-memory "
                           "atomic per (32-pixel mask word, angle, rho bin), not one per vote, so its binding resource is not the atomic "
-                          "unit (gatomics_per_s against smem_atomic_peak_gops) but the XU pipe that evaluates cvRound(x cos + y sin): "
-                          "see the ncu XU utilisation in profiles/"},
+                          "unit (gatomics_per_s against smem_atomic_peak_gops) but instruction issue: cvRound(x cos + y sin) per "
+                          "(word, angle), FP32 magic-number conversions since round 2 instead of the XU pipe (profiles/r02_sass_summary.md)"},
         "counters": counters,
         "cpu_baseline": cpu_baseline,
         "dropin_e2e": dropin,
@@ -975,8 +935,8 @@ def run_ours_config5(args):
             "clocks": clocks, "gpu_launches": h.kernel_launches() - launches0,
             "verified": verified if not args.no_verify else None, "cases_total": len(cases),
             "roofline": {"bound": "hbm", "kernel": "k_hough_vote", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "the vote kernel is bound by the XU pipe / shared-memory atomics, not by HBM; see gvotes_per_s, gatomics_per_s "
-                                 "against smem_atomic_peak_gops and the ncu XU utilisation in profiles/"},
+                         "note": "the vote kernel is bound by instruction issue / shared-memory atomics, not by HBM; see gvotes_per_s, gatomics_per_s "
+                                 "against smem_atomic_peak_gops and the ncu summaries in profiles/ (r02n_hough_c4_*)"},
             "smem_atomic_peak_gops": smem_peak,
             "gvotes_per_s_rho20_mean": float(np.mean([r["gvotes_per_s"] for r in base])) if base else None,
             "gvotes_per_s_rho1_mean": float(np.mean([r["gvotes_per_s"] for r in fine])) if fine else None,
@@ -984,6 +944,91 @@ def run_ours_config5(args):
     print(json.dumps(line))
     h.close()
     return 0
+
+
+HBM_STAGE_KERNELS = ("k_prep", "k_morph_march", "k_nms_march")
+_STAGE_OF = {"k_nms_march": "sobel+nms", "k_morph_march": "lut+morph"}
+
+
+def _base(kernel):
+    return kernel.split("(")[0]
+
+
+def build_roofline(ktable, peak, peak_src, measured, measured_src, stage_ms, n_serial, bracketed_ms_per_step):
+    """The `roofline` object of the JSON line from the table of bracketed kernels (one row per kernel function, pass and
+    labelling kind: kernel, pass, ms_per_step, launches_per_step and, where SURVEY.md 8(d) has a byte figure,
+    alg_bytes_per_step / design_bytes_per_step).
+
+    The kernel named is the one that carries the most bracketed time of the step, all its launches together (both passes,
+    all batch parts, fg and bg labelling) - whichever stage it belongs to; `hbm_stage` repeats the same figures for the
+    time-dominant kernel of the streaming stages (prep / morphology / Sobel+NMS), which is where HBM could bind."""
+    measured = measured or {}
+    for e in ktable:
+        e["avg_launch_ms"] = e["ms_per_step"] / max(e["launches_per_step"], 1)
+        if "alg_bytes_per_step" in e and e["ms_per_step"] > 0:
+            e["gbs"] = e["alg_bytes_per_step"] / (e["ms_per_step"] * 1e6)
+            e["frac_of_hbm_peak"] = e["gbs"] / peak
+            e["frac_of_hbm_peak_design_bytes"] = e["design_bytes_per_step"] / (e["ms_per_step"] * 1e6) / peak
+        if _base(e["kernel"]) in measured:
+            e["dram_bytes_per_step_measured_both_passes"] = measured[_base(e["kernel"])]
+    ktable = sorted(ktable, key=lambda e: -e["ms_per_step"])
+    tot = {}
+    for e in ktable:
+        tot[_base(e["kernel"])] = tot.get(_base(e["kernel"]), 0.0) + e["ms_per_step"]
+
+    def describe(dom):
+        rows = [e for e in ktable if _base(e["kernel"]) == dom]
+        ms = sum(e["ms_per_step"] for e in rows)
+        nl = sum(e["launches_per_step"] for e in rows)
+        out = {"kernel": dom, "ms_per_step": ms, "launches_per_step": nl, "avg_launch_ms": ms / max(nl, 1),
+               "traffic": (measured[dom] / nl) if dom in measured and nl else None}
+        if all("alg_bytes_per_step" in e for e in rows) and ms > 0:
+            ab = sum(e["alg_bytes_per_step"] for e in rows)
+            db = sum(e["design_bytes_per_step"] for e in rows)
+            out.update(survey_bytes_per_launch=ab / nl, design_bytes_per_launch=db / nl,
+                       frac_survey_bytes=ab / (ms * 1e6) / peak, frac_design_bytes=db / (ms * 1e6) / peak)
+            if dom in _STAGE_OF:      # the same kernel with nothing else on the GPU: stage brackets of the serialised steps
+                ms_alone = sum(m for n_, m in stage_ms if n_.split(":")[-1].startswith(_STAGE_OF[dom]))
+                if ms_alone > 0:
+                    out["alone"] = {"ms_per_step": ms_alone, "gbs": ab / (ms_alone * 1e6), "frac": ab / (ms_alone * 1e6) / peak,
+                                    "frac_design_bytes": db / (ms_alone * 1e6) / peak,
+                                    "how": "CUDA-event stage brackets of the %d steps run with LFD_SERIAL_PASSES (one stream, one launch per pass)" % n_serial}
+        elif dom in measured and ms > 0:      # no byte figure in SURVEY.md 8(d) for this kernel: the DRAM bytes ncu measured
+            out.update(design_bytes_per_launch=measured[dom] / nl, frac_design_bytes=measured[dom] / (ms * 1e6) / peak,
+                       bytes_model="measured DRAM bytes of the committed ncu list (SURVEY.md 8(d) has no byte figure for this kernel)")
+        return out
+
+    dom = describe(max(tot, key=lambda k: tot[k]))
+    hbm = describe(max((k for k in tot if k in HBM_STAGE_KERNELS), key=lambda k: tot[k]))
+    # `frac`: SURVEY.md 8(d)'s algorithmic bytes where the stage streams planes the way the survey counts them (prep,
+    # morphology, Sobel+NMS); for the run-based labelling (and kernels the survey gives no bytes for) the survey's int32 label
+    # planes are never materialised, so the bytes this design has to move are the algorithmic bytes of the kernel
+    use_survey = dom["kernel"] in HBM_STAGE_KERNELS and "frac_survey_bytes" in dom
+    frac = dom.get("frac_survey_bytes") if use_survey else dom.get("frac_design_bytes")
+    per_launch = dom.get("survey_bytes_per_launch") if use_survey else dom.get("design_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": dom["kernel"],
+                "achieved": (per_launch / (dom["avg_launch_ms"] * 1e6)) if per_launch else None, "peak": peak, "unit": "GB/s",
+                "frac": frac, "frac_design_bytes": dom.get("frac_design_bytes"), "frac_survey_bytes": dom.get("frac_survey_bytes"),
+                "algorithmic_bytes_per_launch": per_launch, "bytes_model": dom.get("bytes_model", "SURVEY.md 8(d)" if use_survey else "design bytes (see note)"),
+                "design_bytes_per_launch": dom.get("design_bytes_per_launch"), "survey_bytes_per_launch": dom.get("survey_bytes_per_launch"),
+                "traffic": dom["traffic"], "traffic_source": measured_src, "peak_source": peak_src,
+                "avg_launch_ms": dom["avg_launch_ms"], "launches_per_step": dom["launches_per_step"], "ms_per_step": dom["ms_per_step"],
+                "bracketed_ms_per_step": bracketed_ms_per_step, "alone": dom.get("alone"),
+                "hbm_stage": hbm,
+                "all_kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])},
+                "note": "`kernel` is the kernel function with the most bracketed time per step, all its launches together (both "
+                        "passes, all batch parts, fg and bg labelling); `hbm_stage` is the time-dominant kernel of the streaming "
+                        "stages (prep / morphology / Sobel+NMS) with the same figures. frac_survey_bytes uses SURVEY.md 8(d)'s "
+                        "algorithmic bytes (every stage charged one read of its input and one write of its output: LUT apply, erode "
+                        "and dilate are three stages there and one pass over the plane here; labelling is charged two int32 label "
+                        "planes that a run-based labelling never writes), frac_design_bytes the bytes this design has to move; "
+                        "`frac` is the survey figure for the streaming kernels and the design figure otherwise. Durations are CUDA "
+                        "events recorded on the launching stream around every launch inside the captured graph, over a second run "
+                        "of the same K steps (bracketed_ms_per_step; the event nodes cost a few % so the headline region runs "
+                        "without them), with the other three streams running - a launch timed alone is shorter "
+                        "(profiles/*ktiming*, profiles/*launch_shares*). No kernel behind k_prep is HBM-bound: the step is "
+                        "instruction-issue / latency bound (profiles/inst_*_summary.txt, DESIGN.md 3). `kernels` lists every bracketed kernel."}
+    return roofline, ktable
 
 
 def main():

@@ -3,7 +3,7 @@
 
 usage: python profiles/summarize.py <round tag> <launches.csv> <raw.csv> <plain_profile.json> [batch]
   launches.csv : ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...
-  raw.csv      : ncu -i prof.ncu-rep --page raw --csv
+  raw.csv      : ncu -i prof.ncu-rep --page raw --csv   ('-' = launch list only)
 """
 import collections
 import csv
@@ -39,6 +39,8 @@ with open(out_md, "w") as f:
     for s in pl["stages"]:
         f.write("| %s | %.3f | %.1f%% |\n" % (s["stage"], s["ms_per_step"], 100 * s["ms_per_step"] / ts))
 print("wrote", out_md)
+if raw == "-":              # launch list only (profiles/launch_list.sh)
+    sys.exit(0)
 
 rows = list(csv.reader(open(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
