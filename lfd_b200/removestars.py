@@ -5,7 +5,6 @@ Mirrors /root/reference/lfd/detecttrails/removestars.py: ``read_photoObj`` (:63-
 ``remove_stars`` (:148-233) keep their names, arguments and return values; the deprecated CSV
 functions (:19-60, :135-145) are unreachable from ``process_field`` and are not provided.
 """
-import math
 
 import numpy as np
 

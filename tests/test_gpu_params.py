@@ -7,7 +7,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from lfd_b200 import synth
-from oracle import cv_restate as cr
 from oracle import ref_pipeline as rp
 
 

@@ -2,7 +2,6 @@
 result decoding, and the C-ABI library's symbols (no compute calls without a GPU)."""
 import ctypes
 import os
-import re
 
 import numpy as np
 import pytest
